@@ -1,0 +1,107 @@
+"""Generate tests/golden/*.safetensors from the UNMODIFIED reference modules
+(TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+Run in the build container (where /root/reference exists):   python -m oracle.make_golden
+The reference cannot travel to the GPU box, so its outputs on small seeded cases are committed as
+fixtures.  Each fixture holds the outputs of the reference's own `Transformer.forward` /
+`generate` (mistral_inference/transformer.py:221-242, generate.py:43-148) imported behind
+oracle/ref_shims.py, on weights from mistral_inference_b200.synth (bit-reproducible anywhere).
+
+Cases follow SURVEY.md section 8c "tests to carry over": ragged batch greedy decode; ring that
+wraps (sliding_window < length); list-valued sliding_window; 8-expert top-2 MoE;
+max_batch_size > B; chunked re-prefill (the reference's own consistency property).
+"""
+import json
+import sys
+from pathlib import Path
+from typing import Dict, List
+
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+from mistral_inference_b200 import synth  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+GOLDEN_DIR = REPO / "tests" / "golden"
+
+# name -> (shape name, param overrides, dtype, prompts (lengths), max_tokens, max_batch_size, chunk_size for re-prefill)
+CASES: Dict[str, dict] = {
+    "dense_full": dict(shape="tiny", over={}, dtype="bfloat16", prompt_lens=[8, 4, 4, 4], max_tokens=7, max_batch=4, chunk=None),
+    "dense_w4_chunk5": dict(shape="tiny", over={"sliding_window": 4}, dtype="bfloat16", prompt_lens=[8, 10], max_tokens=8,
+                            max_batch=3, chunk=5),
+    "dense_wlist": dict(shape="tiny", over={"sliding_window": [3, None]}, dtype="bfloat16", prompt_lens=[8, 10], max_tokens=8,
+                        max_batch=2, chunk=5),
+    "moe_full": dict(shape="tiny-moe", over={}, dtype="bfloat16", prompt_lens=[9, 7, 8], max_tokens=6, max_batch=3, chunk=4),
+    "moe_w4": dict(shape="tiny-moe", over={"sliding_window": 4}, dtype="bfloat16", prompt_lens=[9, 7], max_tokens=6, max_batch=2,
+                   chunk=4),
+    "dense_full_fp32": dict(shape="tiny", over={}, dtype="float32", prompt_lens=[8, 4, 4, 4], max_tokens=7, max_batch=4, chunk=None),
+}
+
+
+def case_inputs(case: dict, seed: int):
+    p = synth.shape(case["shape"], **case["over"])
+    prompts = [synth.synth_prompt(n, p["vocab_size"], seed * 100 + i) for i, n in enumerate(case["prompt_lens"])]
+    return p, prompts
+
+
+def run_reference(case: dict, seed: int = 1) -> Dict[str, torch.Tensor]:
+    ref = ref_shims.import_reference()
+    p, prompts = case_inputs(case, seed)
+    dtype = getattr(torch, case["dtype"])
+    args = ref.args.TransformerArgs.from_dict(dict(p))
+    args.max_batch_size = case["max_batch"]
+    with torch.device("meta"):
+        model = ref.transformer.Transformer(args)
+    model.load_state_dict(synth.synth_state_dict(p, seed, dtype), assign=True, strict=True)
+    model = model.to(device="cpu", dtype=dtype).eval()
+
+    recorded: List[torch.Tensor] = []
+    orig_forward = model.forward
+
+    def recording_forward(*a, **kw):
+        out = orig_forward(*a, **kw)
+        recorded.append(out.clone())
+        return out
+
+    model.forward = recording_forward  # instance attribute; the reference code itself is untouched
+    toks, logprobs = ref.generate.generate(prompts, model, max_tokens=case["max_tokens"], temperature=0.0)
+    out: Dict[str, torch.Tensor] = {}
+    out["prefill_logits"] = recorded[0]  # [sum(prompt_lens), V] fp32
+    out["decode_logits"] = torch.stack(recorded[1:], 0)  # [max_tokens, B, V] fp32 (last one is never sampled)
+    out["tokens"] = torch.tensor(toks, dtype=torch.int64)
+    out["logprobs"] = torch.tensor(sum(logprobs, []), dtype=torch.float64)
+    # the reference's own consistency check: re-prefill prompt+generated (optionally chunked), max_tokens=0
+    recorded.clear()
+    full = [pr + t for pr, t in zip(prompts, toks)]
+    gen2, logprobs2 = ref.generate.generate(full, model, max_tokens=0, temperature=0.0, chunk_size=case["chunk"])
+    assert gen2 == []
+    out["reprefill_logprobs"] = torch.tensor(sum(logprobs2, []), dtype=torch.float64)
+    out["reprefill_logits"] = torch.cat(recorded, 0)  # chunks concatenated in call order
+    return out
+
+
+def main() -> None:
+    GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
+    import safetensors.torch
+
+    for name, case in CASES.items():
+        out = run_reference(case)
+        # the reference's property, on the reference itself (fp32 bound of tests/test_generate.py:63 is 5e-4; bf16 is looser)
+        n = min(len(out["logprobs"]), len(out["reprefill_logprobs"]))
+        meta = {
+            "case": json.dumps(case),
+            "seed": "1",
+            "torch": torch.__version__,
+            "cpu_capability": torch.backends.cpu.get_cpu_capability(),
+            "reference": "mistralai/mistral-inference@2557e12 (v1.6.0) modules, unmodified, via oracle/ref_shims.py",
+        }
+        safetensors.torch.save_file({k: v.contiguous() for k, v in out.items()}, str(GOLDEN_DIR / f"{name}.safetensors"), metadata=meta)
+        print(f"{name}: tokens={out['tokens'].tolist()} prefill_logits={tuple(out['prefill_logits'].shape)} "
+              f"bytes={sum(v.numel() * v.element_size() for v in out.values())} n_logprobs={n}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""Shared helpers for the parity tests."""
+import json
+from pathlib import Path
+from typing import Dict, List, Tuple
+
+import torch
+
+from mistral_inference_b200 import synth
+from oracle import restatement as R
+
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.safetensors"))
+
+
+def load_golden(name: str) -> Tuple[dict, Dict[str, torch.Tensor], dict]:
+    import safetensors
+    import safetensors.torch
+
+    path = str(GOLDEN_DIR / f"{name}.safetensors")
+    tensors = safetensors.torch.load_file(path)
+    with safetensors.safe_open(path, "pt") as f:
+        meta = f.metadata()
+    return json.loads(meta["case"]), tensors, meta
+
+
+def case_params_prompts(case: dict, seed: int = 1) -> Tuple[dict, List[List[int]]]:
+    p = synth.shape(case["shape"], **case["over"])
+    prompts = [synth.synth_prompt(n, p["vocab_size"], seed * 100 + i) for i, n in enumerate(case["prompt_lens"])]
+    return p, prompts
+
+
+def oracle_args(p: dict, max_batch: int) -> R.OracleArgs:
+    moe = p.get("moe") or {}
+    return R.OracleArgs(dim=p["dim"], n_layers=p["n_layers"], head_dim=p["head_dim"], hidden_dim=p["hidden_dim"],
+                        n_heads=p["n_heads"], n_kv_heads=p["n_kv_heads"], norm_eps=p["norm_eps"], vocab_size=p["vocab_size"],
+                        max_batch_size=max_batch, rope_theta=p.get("rope_theta"), num_experts=moe.get("num_experts", 0),
+                        num_experts_per_tok=moe.get("num_experts_per_tok", 0), sliding_window=p.get("sliding_window"))
+
+
+def oracle_model(p: dict, max_batch: int, seed: int = 1, dtype=torch.bfloat16) -> R.OracleTransformer:
+    return R.OracleTransformer(oracle_args(p, max_batch), synth.synth_state_dict(p, seed, dtype))
+
+
+def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """|a-b| in units of bf16 ulps, per element (a, b bf16 or values that were rounded to bf16)."""
+    a16 = a.to(torch.bfloat16).view(torch.int16).to(torch.int32)
+    b16 = b.to(torch.bfloat16).view(torch.int16).to(torch.int32)
+    # map sign-magnitude to a monotonic integer line
+    a16 = torch.where(a16 < 0, -(a16 & 0x7FFF), a16)
+    b16 = torch.where(b16 < 0, -(b16 & 0x7FFF), b16)
+    return (a16 - b16).abs()
+
+
+def same_machine_as_golden(meta: dict) -> bool:
+    return meta.get("torch") == torch.__version__ and meta.get("cpu_capability") == torch.backends.cpu.get_cpu_capability()
