@@ -1,0 +1,147 @@
+/*
+ * mistral_b200.h -- C ABI of libmb200.so: the sm_100a implementation of the mistral-inference
+ * transformer hot path (Attention block + FeedForward/MoE block + the norm / lm-head either side).
+ *
+ * The reference (mistralai/mistral-inference @ 2557e12) is pure Python and has NO FFI / plugin
+ * boundary; its hot path is a sequence of torch / xformers library calls.
+ * Each entry point below replaces one group of those call sites and cites them.  The reference-side
+ * binding is a ctypes stub; in this repo the caller is
+ * mistral_inference_b200/_abi.py, which mirrors the reference's Python API on top.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only.  Every `*_d` / `const void*` tensor argument is a DEVICE pointer
+ *     (torch: tensor.data_ptr()); bf16 tensors are raw 16-bit words, row-major, innermost contiguous.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all work is
+ *     enqueued on it; no entry point synchronises, allocates or frees device memory, or touches host
+ *     copies of the data.  Scratch comes from the caller-provided `workspace` (device, 256-B aligned).
+ *   - returns 0 on success, a negative MB200_E_* code otherwise; mb200_last_error() gives the
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - integer metadata (positions, rows, lengths) are int32 device arrays.
+ *   - head_dim must be 128 (every config in BASELINE.json); dims must be multiples of 8 (16-byte rows).
+ */
+#ifndef MISTRAL_B200_H_
+#define MISTRAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_ABI_VERSION 1
+
+#define MB200_OK 0
+#define MB200_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define MB200_E_WORKSPACE (-2) /* workspace too small */
+#define MB200_E_CUDA (-3)      /* CUDA runtime / driver error at launch */
+
+int mb200_abi_version(void);
+const char* mb200_last_error(void);
+/* Number of SMs / max opt-in shared memory of the current device (for the host-side planners). */
+int mb200_device_info(int* sm_count, int* max_smem_optin);
+
+/* ---------------------------------------------------------------------------------------------
+ * RMSNorm.  out = bf16( bf16( x_f32 * rsqrt(mean(x_f32^2) + eps) ) * w )
+ * Replaces RMSNorm.forward (transformer_layers.py:115-120; call sites :165,:167, transformer.py:219).
+ * x, out: [T, dim] bf16; w: [dim] bf16.
+ */
+int mb200_rmsnorm(const void* x, const void* w, void* out, int64_t T, int64_t dim, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention input: RMSNorm -> packed QKV projection -> interleaved-pair RoPE (q,k) -> optional
+ * scatter of k,v into the rotating KV cache.
+ * Replaces attention_norm + wq/wk/wv + apply_rotary_emb + CacheView.update
+ * (transformer_layers.py:165,66-70; rope.py:13-23; cache.py:83-92).
+ *   x          [T, dim] bf16 (block input, un-normed)
+ *   norm_w     [dim] bf16
+ *   wqkv       [(H + 2*KV) * hd, dim] bf16: rows = wq ++ wk ++ wv ([out, in] like nn.Linear)
+ *   rope       [n_pos, hd/2, 2] fp32 = view_as_real(precompute_freqs_cis(...)) (rope.py:6-10)
+ *   positions  [T] int32 absolute positions (cache.py:228-230)
+ *   q_out      [T, H*hd] bf16; k_out, v_out [T, KV*hd] bf16 (rotated k, raw v)
+ *   cache_k/v  [n_rows, KV, hd] bf16 flat ring (cache.py:88-89) and cache_rows [T] int32 = slot + b*W
+ *              (cache.py:235) or -1 for tokens that are not cached (to_cache_mask false, cache.py:226).
+ *              Pass cache_rows = NULL to skip the scatter (prefill reads the old ring first:
+ *              transformer_layers.py:75-76; use mb200_kv_ring_write afterwards).
+ * T <= MB200_SKINNY_MAX_T uses the weight-streaming GEMV path (HBM-bound), larger T the tensor-core path.
+ * workspace: >= mb200_workspace_bytes(...) for this T.
+ */
+int mb200_attn_qkv(const void* x, const void* norm_w, const void* wqkv, const float* rope, const int32_t* positions,
+                   void* q_out, void* k_out, void* v_out, void* cache_k, void* cache_v, const int32_t* cache_rows,
+                   int64_t T, int64_t dim, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, float eps,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* CacheView.update on its own (cache.py:83-92): rows[t] >= 0 ? cache[rows[t]] = src[t]. */
+int mb200_kv_ring_write(const void* k_new, const void* v_new, void* cache_k, void* cache_v, const int32_t* cache_rows,
+                        int64_t T, int64_t n_kv_heads, int64_t head_dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GQA decode attention over the rotating cache (one query token per sequence).
+ * Replaces cache.key/value + repeat_kv + memory_efficient_attention with
+ * BlockDiagonalCausalWithOffsetPaddedKeysMask (transformer_layers.py:78-88, cache.py:250-254):
+ * sequence b attends to ring slots [0, kv_len[b]) of its ring, kv_len = min(pos+1, W); order-free softmax.
+ *   q [B, H*hd] bf16; cache_k/v [max_batch, W, KV, hd] bf16; kv_len [B] int32 (device); out [B, H*hd] bf16
+ *   n_splits: KV range is cut into this many CTAs per (b, kv head) (flash-decoding), combined in-kernel.
+ */
+int mb200_attn_decode(const void* q, const void* cache_k, const void* cache_v, const int32_t* kv_len, void* out,
+                      int64_t B, int64_t W, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int64_t n_splits,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Prefill attention (varlen, causal, sliding window) reading old keys from the ring and new keys from
+ * k_new/v_new.  Replaces interleave_kv + repeat_kv + memory_efficient_attention with
+ * BlockDiagonalCausalMask.make_local_attention / BlockDiagonalMask.make_local_attention_from_bottomright
+ * (transformer_layers.py:75-76,84-88; cache.py:94-117,240,243-248).
+ * Query i of sequence b sits at absolute position p = seqpos[b] + i and attends to absolute positions
+ * (p - W, p]; positions < seqpos[b] come from ring slot (pos % W), the rest from the new chunk.
+ *   q [T, H*hd]; k_new, v_new [T, KV*hd]; cache_k/v [max_batch, W, KV, hd]; out [T, H*hd] (all bf16)
+ *   q_start [B+1] int32 (prefix sums of seqlens), seqpos [B] int32 (tokens already cached) -- device arrays
+ *   max_seqlen: max over b of seqlens[b] (grid sizing);  window = W (cache size of this layer)
+ *   causal = 0: the cache-less forward (transformer_layers.py:72-73,88 with mask=None): every query attends
+ *               to every new key of the whole flattened batch; ring, q_start, seqpos are ignored.
+ */
+int mb200_attn_prefill(const void* q, const void* k_new, const void* v_new, const void* cache_k, const void* cache_v,
+                       const int32_t* q_start, const int32_t* seqpos, void* out, int64_t T, int64_t B, int64_t max_seqlen,
+                       int64_t W, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * out = residual + bf16( x @ W^T )   (bf16 add, one more rounding).
+ * Replaces wo + residual (transformer_layers.py:93,166) and w2 + residual (:106,:168).
+ *   x [T, K]; w [N, K]; residual, out [T, N] (out may alias residual).  residual = NULL: plain linear.
+ */
+int mb200_linear_residual(const void* x, const void* w, const void* residual, void* out, int64_t T, int64_t N, int64_t K,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused FFN input: RMSNorm -> packed gate/up projection -> bf16(silu(a)) * b.
+ * Replaces ffn_norm + w1, w3, silu, mul (transformer_layers.py:167,106).
+ *   x [T, dim]; norm_w [dim] (NULL = x is already normed, used by MoE experts);
+ *   w13 [2*hidden, dim]: row 2i = w1[i] (gate), row 2i+1 = w3[i] (up);  g_out [T, hidden]
+ */
+int mb200_ffn_gateup(const void* x, const void* norm_w, const void* w13, void* g_out, int64_t T, int64_t dim,
+                     int64_t hidden, float eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Final RMSNorm + lm head, fp32 logits.  Replaces norm + output + .float() (transformer.py:219,235,240).
+ *   x [T, dim]; norm_w [dim]; w_out [V, dim]; logits [T, V] fp32 (each value is a bf16-rounded number).
+ */
+int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* logits, int64_t T, int64_t dim,
+                  int64_t vocab, float eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Upper bound of the scratch any entry point above needs for up to T tokens of this geometry. */
+size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
+                             int64_t hidden, int64_t vocab, int64_t max_batch);
+
+#define MB200_SKINNY_MAX_T 4
+
+/* Workspace contract: the first 64 KiB of `workspace` hold self-resetting counters; the caller zero-fills the
+ * workspace ONCE when allocating it (torch.zeros) and never writes to it afterwards. */
+#define MB200_WORKSPACE_HEADER_BYTES (64 * 1024)
+
+/* Test-only: CUDA-core fp32 GEMM c[T, N] = a[T, K] w[N, K]^T used to cross-check the tensor-core kernels. */
+int mb200_test_gemm_naive(const void* a, const void* w, float* c, int64_t T, int64_t N, int64_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISTRAL_B200_H_ */

@@ -1,1 +1,21 @@
-"""B200-native drop-in for the mistral-inference transformer hot path."""
+"""B200-native drop-in for the mistral-inference transformer hot path.
+
+Public API mirrors mistral_inference: `Transformer.from_folder / forward / forward_partial`,
+`generate`, `BufferCache`, `TransformerArgs`.  All compute runs in libmb200.so (hand-written sm_100a
+CUDA behind the C ABI in include/mistral_b200.h); importing this package does not load the library,
+using the model does -- and fails loudly if it is missing.
+"""
+from .args import MoeArgs, TransformerArgs  # noqa: F401
+from .cache import BufferCache  # noqa: F401
+
+
+def __getattr__(name):  # lazy: keep `import mistral_inference_b200.synth` light
+    if name == "Transformer":
+        from .transformer import Transformer
+
+        return Transformer
+    if name == "generate":
+        from .generate import generate
+
+        return generate
+    raise AttributeError(name)

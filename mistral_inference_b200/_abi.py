@@ -1,0 +1,175 @@
+"""ctypes binding of libmb200.so (C ABI: include/mistral_b200.h).
+
+This is the only place Python touches the native library.  There is NO fallback: if the library is
+missing or a call fails, an exception is raised (the product path never routes through PyTorch
+reference math or the CPU oracle).
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmb200.so"
+_lib: Optional[ctypes.CDLL] = None
+
+ABI_VERSION = 1
+SKINNY_MAX_T = 4
+WORKSPACE_HEADER_BYTES = 64 * 1024
+
+# name -> (restype, argtypes); mirrors include/mistral_b200.h declaration by declaration
+_SIGNATURES = {
+    "mb200_abi_version": (c_int, []),
+    "mb200_last_error": (c_char_p, []),
+    "mb200_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "mb200_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p]),
+    "mb200_attn_qkv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
+    "mb200_kv_ring_write": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "mb200_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                  c_int64, c_void_p, c_size_t, c_void_p]),
+    "mb200_attn_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "mb200_linear_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "mb200_ffn_gateup": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t,
+                                 c_void_p]),
+    "mb200_lm_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t,
+                              c_void_p]),
+    "mb200_workspace_bytes": (c_size_t, [c_int64] * 8),
+    "mb200_test_gemm_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+}
+
+
+class Mb200Error(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libmb200.so once.  Raises (never falls back) when it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise Mb200Error(
+            f"{_LIB_PATH} not found: build it with `python -m mistral_inference_b200.build` "
+            "(there is no PyTorch/CPU fallback for the hot path)")
+    handle = ctypes.CDLL(str(_LIB_PATH), mode=os.RTLD_LOCAL if hasattr(os, "RTLD_LOCAL") else 0)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if handle.mb200_abi_version() != ABI_VERSION:
+        raise Mb200Error(f"libmb200 ABI {handle.mb200_abi_version()} != expected {ABI_VERSION}")
+    _lib = handle
+    return handle
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mb200_last_error()
+        raise Mb200Error(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "libmb200 takes contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Workspace:
+    """Caller-owned scratch handed to every entry point (zero-filled once: the first 64 KiB hold self-resetting
+    counters, see MB200_WORKSPACE_HEADER_BYTES)."""
+
+    def __init__(self, nbytes: int, device: torch.device):
+        self.buf = torch.zeros(max(int(nbytes), WORKSPACE_HEADER_BYTES + 256), dtype=torch.uint8, device=device)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    @property
+    def nbytes(self) -> int:
+        return self.buf.numel()
+
+
+def workspace_bytes(T: int, dim: int, n_heads: int, n_kv_heads: int, head_dim: int, hidden: int, vocab: int, max_batch: int) -> int:
+    return int(lib().mb200_workspace_bytes(T, dim, n_heads, n_kv_heads, head_dim, hidden, vocab, max_batch))
+
+
+def device_info():
+    sm, smem = c_int(0), c_int(0)
+    _check(lib().mb200_device_info(ctypes.byref(sm), ctypes.byref(smem)), "mb200_device_info")
+    return sm.value, smem.value
+
+
+# ----------------------------------------------------------------------------- thin typed wrappers
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    T, dim = x.shape
+    out = torch.empty_like(x) if out is None else out
+    _check(lib().mb200_rmsnorm(_ptr(x), _ptr(w), _ptr(out), T, dim, eps, _stream()), "mb200_rmsnorm")
+    return out
+
+
+def attn_qkv(x, norm_w, wqkv, rope, positions, q_out, k_out, v_out, cache_k, cache_v, cache_rows, n_heads, n_kv_heads, head_dim, eps,
+             ws: Workspace) -> None:
+    T, dim = x.shape
+    _check(lib().mb200_attn_qkv(_ptr(x), _ptr(norm_w), _ptr(wqkv), _ptr(rope), _ptr(positions), _ptr(q_out), _ptr(k_out), _ptr(v_out),
+                                _ptr(cache_k), _ptr(cache_v), _ptr(cache_rows), T, dim, n_heads, n_kv_heads, head_dim, eps, ws.ptr,
+                                ws.nbytes, _stream()), "mb200_attn_qkv")
+
+
+def kv_ring_write(k_new, v_new, cache_k, cache_v, cache_rows, n_kv_heads, head_dim) -> None:
+    _check(lib().mb200_kv_ring_write(_ptr(k_new), _ptr(v_new), _ptr(cache_k), _ptr(cache_v), _ptr(cache_rows), k_new.shape[0],
+                                     n_kv_heads, head_dim, _stream()), "mb200_kv_ring_write")
+
+
+def attn_decode(q, cache_k, cache_v, kv_len, out, n_heads, n_kv_heads, head_dim, n_splits, ws: Workspace) -> None:
+    B = q.shape[0]
+    W = cache_k.shape[1]
+    _check(lib().mb200_attn_decode(_ptr(q), _ptr(cache_k), _ptr(cache_v), _ptr(kv_len), _ptr(out), B, W, n_heads, n_kv_heads, head_dim,
+                                   n_splits, ws.ptr, ws.nbytes, _stream()), "mb200_attn_decode")
+
+
+def attn_prefill(q, k_new, v_new, cache_k, cache_v, q_start, seqpos, out, B, max_seqlen, W, n_heads, n_kv_heads, head_dim,
+                 causal: bool) -> None:
+    _check(lib().mb200_attn_prefill(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(cache_k), _ptr(cache_v), _ptr(q_start), _ptr(seqpos),
+                                    _ptr(out), q.shape[0], B, max_seqlen, W, n_heads, n_kv_heads, head_dim, 1 if causal else 0,
+                                    _stream()), "mb200_attn_prefill")
+
+
+def linear_residual(x, w, residual, out, ws: Workspace) -> None:
+    T, K = x.shape
+    N = w.shape[0]
+    _check(lib().mb200_linear_residual(_ptr(x), _ptr(w), _ptr(residual), _ptr(out), T, N, K, ws.ptr, ws.nbytes, _stream()),
+           "mb200_linear_residual")
+
+
+def ffn_gateup(x, norm_w, w13, g_out, eps, ws: Workspace) -> None:
+    T, dim = x.shape
+    hidden = w13.shape[0] // 2
+    _check(lib().mb200_ffn_gateup(_ptr(x), _ptr(norm_w), _ptr(w13), _ptr(g_out), T, dim, hidden, eps, ws.ptr, ws.nbytes, _stream()),
+           "mb200_ffn_gateup")
+
+
+def lm_head(x, norm_w, w_out, logits, eps, ws: Workspace) -> None:
+    T, dim = x.shape
+    _check(lib().mb200_lm_head(_ptr(x), _ptr(norm_w), _ptr(w_out), _ptr(logits), T, dim, w_out.shape[0], eps, ws.ptr, ws.nbytes,
+                               _stream()), "mb200_lm_head")
+
+
+def test_gemm_naive(a, w) -> torch.Tensor:
+    T, K = a.shape
+    c = torch.empty(T, w.shape[0], dtype=torch.float32, device=a.device)
+    _check(lib().mb200_test_gemm_naive(_ptr(a), _ptr(w), _ptr(c), T, w.shape[0], K, _stream()), "mb200_test_gemm_naive")
+    return c

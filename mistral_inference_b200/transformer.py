@@ -1,0 +1,400 @@
+"""Transformer model shell (API mirror of mistral_inference/transformer.py).
+
+`Transformer.from_folder / forward / forward_partial / load_state_dict` keep the reference's signatures and
+on-disk contract (params.json + consolidated.safetensors | consolidated.00.pth, reference state-dict keys);
+the layer loop calls the fused libmb200 kernels.  bf16 on CUDA only; there is no PyTorch/CPU fallback.
+"""
+import json
+import logging
+import math
+import os
+from pathlib import Path
+from typing import Any, Dict, List, Mapping, Optional, Union
+
+import torch
+from torch import nn
+
+from . import _abi
+from .args import TransformerArgs
+from .cache import BufferCache, CacheInputMetadata
+from .rope import precompute_freqs_cis
+from .transformer_layers import RMSNorm, TransformerBlock
+
+ROPE_TABLE_LEN = 128_000  # transformer.py:116
+
+
+class _OutputView:
+    def __init__(self, model: "Transformer"):
+        self._m = model
+
+    @property
+    def weight(self) -> torch.Tensor:
+        return self._m.output_weight
+
+
+class Transformer(nn.Module):
+    def __init__(self, args: TransformerArgs, pipeline_rank: int = 0, num_pipeline_ranks: int = 1, softmax_fp32: bool = True):
+        super().__init__()
+        self.args = args
+        self.vocab_size = args.vocab_size
+        self.n_layers = args.n_layers
+        self._rope_table: Optional[torch.Tensor] = None
+        assert self.vocab_size > 0
+        assert pipeline_rank < num_pipeline_ranks, (pipeline_rank, num_pipeline_ranks)
+        self.pipeline_rank = pipeline_rank
+        self.num_pipeline_ranks = num_pipeline_ranks
+        self.softmax_fp32 = softmax_fp32
+
+        self.tok_embeddings: Optional[nn.Embedding] = None
+        self.norm: Optional[RMSNorm] = None
+        self.output_weight: Optional[nn.Parameter] = None
+        if pipeline_rank == 0:
+            self.tok_embeddings = nn.Embedding(args.vocab_size, args.dim)
+            self.tok_embeddings.weight.requires_grad_(False)
+        if pipeline_rank == num_pipeline_ranks - 1:
+            self.norm = RMSNorm(args.dim, eps=args.norm_eps)
+            self.output_weight = nn.Parameter(torch.empty(args.vocab_size, args.dim), requires_grad=False)
+        # contiguous layer ranges per pipeline rank, keyed by GLOBAL layer id (transformer.py:94-98)
+        num_layers_per_rank = math.ceil(self.n_layers / self.num_pipeline_ranks)
+        offset = self.pipeline_rank * num_layers_per_rank
+        end = min(self.n_layers, offset + num_layers_per_rank)
+        self.layers = nn.ModuleDict({
+            str(i): TransformerBlock(dim=args.dim, hidden_dim=args.hidden_dim, n_heads=args.n_heads, n_kv_heads=args.n_kv_heads,
+                                     head_dim=args.head_dim, norm_eps=args.norm_eps, lora=args.lora, moe=args.moe)
+            for i in range(offset, end)
+        })
+        self.n_local_layers = len(self.layers)
+        self._ws: Optional[_abi.Workspace] = None
+        self._ws_tokens = 0
+        self._decode_graphs: Dict[Any, Any] = {}
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    @property
+    def output(self) -> _OutputView:
+        return _OutputView(self)
+
+    @property
+    def freqs_cis(self) -> torch.Tensor:
+        """complex64 [128000, hd/2] on the model device (transformer.py:108-120)."""
+        return torch.view_as_complex(self.rope_table)
+
+    @property
+    def rope_table(self) -> torch.Tensor:
+        """fp32 [128000, hd/2, 2] (cos, sin): the same bits as the reference's table, built on the CPU."""
+        if self._rope_table is None:
+            theta = self.args.rope_theta or 1000000.0
+            self._rope_table = torch.view_as_real(precompute_freqs_cis(self.args.head_dim, ROPE_TABLE_LEN, theta)).contiguous()
+        if self._rope_table.device != self.device:
+            self._rope_table = self._rope_table.to(device=self.device)
+        return self._rope_table
+
+    def workspace(self, num_tokens: int) -> _abi.Workspace:
+        if self._ws is None or self._ws_tokens < num_tokens or self._ws.buf.device != self.device:
+            a = self.args
+            need = _abi.workspace_bytes(num_tokens, a.dim, a.n_heads, a.n_kv_heads, a.head_dim, a.hidden_dim, a.vocab_size,
+                                        max(a.max_batch_size, 1))
+            self._decode_graphs = {}  # captured graphs hold the old workspace pointer
+            self._ws = _abi.Workspace(need, self.device)
+            self._ws_tokens = num_tokens
+        return self._ws
+
+    # ------------------------------------------------------------------ forward
+    def _check_runnable(self) -> None:
+        if self.device.type != "cuda" or self.dtype != torch.bfloat16:
+            raise _abi.Mb200Error(f"the libmb200 hot path runs bf16 on CUDA only (got {self.dtype} on {self.device}); no fallback exists")
+
+    @torch.inference_mode()
+    def forward_partial(self, input_ids: torch.Tensor, seqlens: List[int], cache: Optional[BufferCache] = None,
+                        images: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        """Local forward pass (transformer.py:163-219): hidden states of this stage; the last stage returns
+        the normalised final embeddings."""
+        assert not images, "vision inputs are outside the accelerated hot path"
+        self._check_runnable()
+        assert len(seqlens) <= self.args.max_batch_size, f"Max batch size is {self.args.max_batch_size}, got batch size of {len(seqlens)}"
+        (num_toks,) = input_ids.shape
+        assert sum(seqlens) == num_toks, (sum(seqlens), num_toks)
+        ws = self.workspace(num_toks)
+
+        input_metadata: Optional[List[CacheInputMetadata]] = None
+        if cache is not None:
+            input_metadata = cache.get_input_metadata(seqlens)
+            positions = input_metadata[0].positions
+        else:
+            positions = torch.cat([torch.arange(0, s, dtype=torch.int32) for s in seqlens]).to(self.device)
+
+        if self.pipeline_rank == 0:
+            assert self.tok_embeddings is not None
+            h = self.tok_embeddings(input_ids)
+        else:
+            h = torch.empty(num_toks, self.args.dim, device=self.device, dtype=self.dtype)
+            torch.distributed.recv(h, src=self.pipeline_rank - 1)
+
+        rope = self.rope_table
+        for local_layer_id, layer in enumerate(self.layers.values()):
+            view = cache.get_view(local_layer_id, input_metadata[local_layer_id]) if cache is not None else None
+            h = layer(h, rope, positions, view, ws)
+
+        if cache is not None:
+            cache.update_seqlens(seqlens)
+        if self.pipeline_rank < self.num_pipeline_ranks - 1:
+            torch.distributed.send(h, dst=self.pipeline_rank + 1)
+            return h
+        assert self.norm is not None
+        return self.norm(h)
+
+    @torch.inference_mode()
+    def forward(self, input_ids: torch.Tensor, seqlens: List[int], cache: Optional[BufferCache] = None,
+                images: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        """transformer.py:221-242.  [T, vocab] logits, fp32 when softmax_fp32."""
+        assert not images, "vision inputs are outside the accelerated hot path"
+        self._check_runnable()
+        last = self.pipeline_rank == self.num_pipeline_ranks - 1
+        if last and self.num_pipeline_ranks == 1:
+            if self._graph_decode_ok(seqlens, cache):
+                outs32 = self.decode_static(input_ids, cache).clone()
+                return outs32 if self.softmax_fp32 else outs32.to(self.dtype)
+            # single stage: final norm + lm head + .float() are one fused call (no [T, dim] normed round trip)
+            h = self._hidden_no_norm(input_ids, seqlens, cache)
+            if cache is not None:
+                cache.update_seqlens(seqlens)
+            outs32 = torch.empty(h.shape[0], self.vocab_size, device=h.device, dtype=torch.float32)
+            assert self.norm is not None and self.output_weight is not None
+            _abi.lm_head(h, self.norm.weight, self.output_weight, outs32, self.args.norm_eps, self.workspace(h.shape[0]))
+            return outs32 if self.softmax_fp32 else outs32.to(self.dtype)
+        h = self.forward_partial(input_ids, seqlens, cache=cache)
+        if not last:
+            outs = torch.empty(h.shape[0], self.vocab_size, device=h.device, dtype=h.dtype)
+        else:
+            assert self.output_weight is not None
+            outs = torch.empty(h.shape[0], self.vocab_size, device=h.device, dtype=h.dtype)
+            _abi.linear_residual(h, self.output_weight, None, outs, self.workspace(h.shape[0]))
+        if self.num_pipeline_ranks > 1:
+            torch.distributed.broadcast(outs, src=self.num_pipeline_ranks - 1)
+        return outs.float() if self.softmax_fp32 else outs
+
+    def _hidden_no_norm(self, input_ids: torch.Tensor, seqlens: List[int], cache: Optional[BufferCache],
+                        input_metadata: Optional[List[CacheInputMetadata]] = None) -> torch.Tensor:
+        assert len(seqlens) <= self.args.max_batch_size, f"Max batch size is {self.args.max_batch_size}, got batch size of {len(seqlens)}"
+        (num_toks,) = input_ids.shape
+        assert sum(seqlens) == num_toks, (sum(seqlens), num_toks)
+        ws = self.workspace(num_toks)
+        if cache is not None:
+            if input_metadata is None:
+                input_metadata = cache.get_input_metadata(seqlens)
+            positions = input_metadata[0].positions
+        else:
+            positions = torch.cat([torch.arange(0, s, dtype=torch.int32) for s in seqlens]).to(self.device)
+        assert self.tok_embeddings is not None
+        h = self.tok_embeddings(input_ids)
+        rope = self.rope_table
+        for local_layer_id, layer in enumerate(self.layers.values()):
+            view = cache.get_view(local_layer_id, input_metadata[local_layer_id]) if cache is not None else None
+            h = layer(h, rope, positions, view, ws)
+        return h
+
+    # ------------------------------------------------------------------ CUDA-graph decode
+    def _graph_decode_ok(self, seqlens: List[int], cache: Optional[BufferCache]) -> bool:
+        if cache is None or self.num_pipeline_ranks != 1 or self.args.moe is not None:
+            return False  # the round-1 MoE layer still has host-side routing syncs
+        if os.environ.get("MB200_DECODE_GRAPH", "1") == "0":
+            return False
+        host = cache._kv_seqlens_host
+        return host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
+
+    def decode_static(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
+        """One decode step for every sequence of `cache` (one new token each) replayed from a CUDA graph: the ~5
+        kernels per layer are enqueued with a single graph launch instead of ~165 Python->C calls.  Returns the
+        graph's STATIC fp32 logits buffer [B, V] (overwritten by the next step).  The first call per
+        (cache, batch) runs eagerly (warm-up), the second captures."""
+        B = tokens.shape[0]
+        seqlens = [1] * B
+        key = (id(cache), B)
+        self.workspace(B)
+        st = self._decode_graphs.get(key)
+        host, layout = cache.build_metadata_host(seqlens)
+        if st is None or st["cache"] is not cache:
+            # warm-up step, eager (also sets function attributes / loads modules outside of capture)
+            st = {"cache": cache, "graph": None,
+                  "tokens": torch.zeros(B, dtype=torch.long, device=self.device),
+                  "meta": torch.zeros(host.shape[0], dtype=torch.int32, device=self.device),
+                  "meta_host": torch.zeros(host.shape[0], dtype=torch.int32).pin_memory(),
+                  "logits": torch.empty(B, self.vocab_size, dtype=torch.float32, device=self.device)}
+            self._decode_graphs[key] = st
+        st["meta_host"].numpy()[:] = host
+        st["meta"].copy_(st["meta_host"], non_blocking=True)
+        st["tokens"].copy_(tokens, non_blocking=True)
+        md = cache.metadata_from_block(st["meta"], layout, seqlens)
+
+        def run() -> None:
+            h = self._hidden_no_norm(st["tokens"], seqlens, cache, md)
+            _abi.lm_head(h, self.norm.weight, self.output_weight, st["logits"], self.args.norm_eps, self.workspace(B))
+
+        if st["graph"] is None and not st.get("warmed"):
+            run()
+            st["warmed"] = True
+        elif st["graph"] is None:
+            self.workspace(B)  # allocate outside of capture
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            st["graph"] = g
+            g.replay()
+        else:
+            st["graph"].replay()
+        cache.update_seqlens(seqlens)
+        return st["logits"]
+
+    # ------------------------------------------------------------------ weights
+    def _assign(self, k: str, v: torch.Tensor) -> bool:
+        """Copies reference-keyed tensor `v` into the packed parameters.  Returns False when the key belongs to
+        another pipeline rank."""
+        def put(dst: torch.Tensor) -> None:
+            assert dst.shape == v.shape, f"{k}: shape {tuple(v.shape)} != expected {tuple(dst.shape)}"
+            dst.copy_(v)
+
+        if k == "tok_embeddings.weight":
+            if self.tok_embeddings is None:
+                return False
+            put(self.tok_embeddings.weight)
+        elif k == "norm.weight":
+            if self.norm is None:
+                return False
+            put(self.norm.weight)
+        elif k == "output.weight":
+            if self.output_weight is None:
+                return False
+            put(self.output_weight)
+        elif k.startswith("layers."):
+            _, lid, rest = k.split(".", 2)
+            if lid not in self.layers:
+                return False
+            blk: TransformerBlock = self.layers[lid]  # type: ignore[assignment]
+            att = blk.attention
+            if rest == "attention.wq.weight":
+                put(att.wqkv[: att.q_dim])
+            elif rest == "attention.wk.weight":
+                put(att.wqkv[att.q_dim: att.q_dim + att.kv_dim])
+            elif rest == "attention.wv.weight":
+                put(att.wqkv[att.q_dim + att.kv_dim:])
+            elif rest == "attention.wo.weight":
+                put(att.wo_weight)
+            elif rest == "attention_norm.weight":
+                put(blk.attention_norm.weight)
+            elif rest == "ffn_norm.weight":
+                put(blk.ffn_norm.weight)
+            elif rest == "feed_forward.gate.weight":
+                put(blk.feed_forward.gate_weight)
+            else:
+                parts = rest.split(".")
+                if parts[0] != "feed_forward":
+                    raise ValueError(f"Unexpected key {k}")
+                ff = blk.feed_forward
+                if parts[1] == "experts":
+                    ff = ff.experts[int(parts[2])]
+                    parts = parts[2:]
+                name = parts[1]
+                if name == "w1":
+                    put(ff.w13.view(ff.hidden_dim, 2, ff.dim)[:, 0])
+                elif name == "w3":
+                    put(ff.w13.view(ff.hidden_dim, 2, ff.dim)[:, 1])
+                elif name == "w2":
+                    put(ff.w2_weight)
+                else:
+                    raise ValueError(f"Unexpected key {k}")
+        else:
+            raise ValueError(f"Unexpected key {k}")
+        return True
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False) -> None:  # type: ignore[override]
+        """Takes a REFERENCE-keyed state dict (transformer.py:244-295), filters by pipeline rank and packs."""
+        del assign  # tensors are copied into the packed buffers
+        loaded = set()
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if self._assign(k, v):
+                    loaded.add(k)
+                else:
+                    logging.debug("Skipping parameter %s at pipeline rank %d", k, self.pipeline_rank)
+        if strict:
+            missing = set(self.reference_keys()) - loaded
+            assert not missing, f"missing keys: {sorted(missing)[:8]}"
+
+    def reference_keys(self) -> List[str]:
+        return list(self.state_dict().keys())
+
+    def state_dict(self, *args: Any, **kwargs: Any) -> Dict[str, torch.Tensor]:  # type: ignore[override]
+        """Reference-keyed views of the packed parameters."""
+        out: Dict[str, torch.Tensor] = {}
+        if self.tok_embeddings is not None:
+            out["tok_embeddings.weight"] = self.tok_embeddings.weight
+        for lid, blk in self.layers.items():
+            p = f"layers.{lid}."
+            att = blk.attention
+            out[p + "attention.wq.weight"] = att.wq.weight
+            out[p + "attention.wk.weight"] = att.wk.weight
+            out[p + "attention.wv.weight"] = att.wv.weight
+            out[p + "attention.wo.weight"] = att.wo_weight
+            out[p + "attention_norm.weight"] = blk.attention_norm.weight
+            out[p + "ffn_norm.weight"] = blk.ffn_norm.weight
+            ff = blk.feed_forward
+            if hasattr(ff, "experts"):
+                out[p + "feed_forward.gate.weight"] = ff.gate_weight
+                for e, ex in enumerate(ff.experts):
+                    for n in ("w1", "w2", "w3"):
+                        out[p + f"feed_forward.experts.{e}.{n}.weight"] = getattr(ex, n).weight
+            else:
+                for n in ("w1", "w2", "w3"):
+                    out[p + f"feed_forward.{n}.weight"] = getattr(ff, n).weight
+        if self.norm is not None:
+            out["norm.weight"] = self.norm.weight
+            out["output.weight"] = self.output_weight
+        return out
+
+    @staticmethod
+    def from_folder(folder: Union[Path, str], max_batch_size: int = 1, num_pipeline_ranks: int = 1,
+                    device: Union[torch.device, str] = "cuda", dtype: Optional[torch.dtype] = None,
+                    softmax_fp32: bool = True) -> "Transformer":
+        """transformer.py:297-338.  Tensors stream from disk straight into the packed device buffers."""
+        with open(Path(folder) / "params.json", "r") as f:
+            model_args = TransformerArgs.from_dict(json.load(f))
+        model_args.max_batch_size = max_batch_size
+        pipeline_rank = torch.distributed.get_rank() if num_pipeline_ranks > 1 else 0
+
+        pt_model_file = Path(folder) / "consolidated.00.pth"
+        safetensors_model_file = Path(folder) / "consolidated.safetensors"
+        assert pt_model_file.exists() or safetensors_model_file.exists(), f"Make sure either {pt_model_file} or {safetensors_model_file} exists"
+        assert not (pt_model_file.exists() and safetensors_model_file.exists()), f"Both {pt_model_file} and {safetensors_model_file} cannot exist"
+
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.device(dev):
+            model = Transformer(model_args, pipeline_rank=pipeline_rank, num_pipeline_ranks=num_pipeline_ranks, softmax_fp32=softmax_fp32)
+        if pt_model_file.exists():
+            loaded = torch.load(str(pt_model_file), mmap=True)
+            ck_dtype = next(iter(loaded.values())).dtype
+            model = model.to(dtype=dtype or ck_dtype)
+            model.load_state_dict(loaded, strict=True)
+        else:
+            import safetensors
+
+            with safetensors.safe_open(str(safetensors_model_file), framework="pt", device="cpu") as f:
+                keys = list(f.keys())
+                ck_dtype = f.get_tensor("norm.weight").dtype if "norm.weight" in keys else f.get_tensor(keys[0]).dtype
+                model = model.to(dtype=dtype or ck_dtype)
+                loaded_keys = set()
+                with torch.no_grad():
+                    for k in keys:
+                        if model._assign(k, f.get_tensor(k)):
+                            loaded_keys.add(k)
+                missing = set(model.reference_keys()) - loaded_keys
+                assert not missing, f"missing keys: {sorted(missing)[:8]}"
+        return model.eval()

@@ -1,0 +1,238 @@
+"""GPU parity, op by op: each C-ABI entry point against the oracle restatement on the same seeded inputs.
+
+Tolerance model (written once here): every output is a bf16 value that the reference produces by rounding an
+fp32 intermediate.  A different fp32 summation order moves that intermediate by ~1e-6 relative, which flips the
+bf16 rounding of a small fraction of elements by ONE ulp.  So: <= 1 bf16 ulp everywhere and >= 97 % bit-identical
+for GEMV/GEMM/elementwise ops; attention outputs get `atol` for near-zero values (cancellation), and the prefill
+kernel 2 ulp because P is rounded to bf16 before the PV tensor-core product (as in any tensor-core attention).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mistral_inference_b200 import _abi
+from mistral_inference_b200.rope import precompute_freqs_cis
+from oracle import restatement as R
+from oracle.attention_ref import attend_block, local_causal_allowed
+
+from .util import assert_bf16_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def ws():
+    return _abi.Workspace(_abi.workspace_bytes(512, 4096, 32, 8, 128, 14336, 32000, 4), torch.device(DEV))
+
+
+@pytest.fixture(scope="module")
+def rope():
+    table = precompute_freqs_cis(128, 8192, 1e6)
+    return table, torch.view_as_real(table).contiguous().to(DEV)
+
+
+@pytest.mark.parametrize("T,dim", [(1, 256), (5, 4096), (33, 5120), (2, 6144)])
+def test_rmsnorm(T, dim):
+    x, w = rnd(T, dim, seed=1, scale=2.0), (1 + 0.2 * rnd(dim, seed=2).float()).to(torch.bfloat16)
+    got = _abi.rmsnorm(x.to(DEV), w.to(DEV), 1e-5)
+    assert_bf16_close(got, R.rms_norm(x, w, 1e-5), max_ulp=1, min_exact=0.995, what="rmsnorm")
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 37, 130])
+@pytest.mark.parametrize("dim,H,KV", [(256, 4, 2), (4096, 32, 8)])
+def test_attn_qkv(T, dim, H, KV, ws, rope):
+    if dim == 4096 and T not in (1, 4, 130):
+        pytest.skip("big shape: representative T only")
+    hd = 128
+    x = rnd(T, dim, seed=3)
+    nw = (1 + 0.2 * rnd(dim, seed=4).float()).to(torch.bfloat16)
+    wq, wk, wv = rnd(H * hd, dim, seed=5, scale=dim ** -0.5), rnd(KV * hd, dim, seed=6, scale=dim ** -0.5), rnd(KV * hd, dim, seed=7, scale=dim ** -0.5)
+    positions = torch.arange(T, dtype=torch.int32) * 37 % 8000
+    table, table_dev = rope
+    # oracle: norm -> three linears -> rope (transformer_layers.py:165,66-70)
+    xn = R.rms_norm(x, nw, 1e-5)
+    q_ref, k_ref = R.apply_rope(F.linear(xn, wq).view(T, H, hd), F.linear(xn, wk).view(T, KV, hd), table[positions.long()])
+    v_ref = F.linear(xn, wv)
+    wqkv = torch.cat([wq, wk, wv], 0).to(DEV)
+    q = torch.empty(T, H * hd, dtype=torch.bfloat16, device=DEV)
+    k = torch.empty(T, KV * hd, dtype=torch.bfloat16, device=DEV)
+    v = torch.empty_like(k)
+    n_rows = 64
+    ck = torch.full((n_rows, KV, hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+    cv = torch.full_like(ck, float("nan"))
+    rows = torch.tensor([(5 * t) % n_rows if t % 3 else -1 for t in range(T)], dtype=torch.int32)
+    if len(set(r for r in rows.tolist() if r >= 0)) < sum(r >= 0 for r in rows.tolist()):
+        rows = torch.tensor([t if t % 3 and t < n_rows else -1 for t in range(T)], dtype=torch.int32)
+    _abi.attn_qkv(x.to(DEV), nw.to(DEV), wqkv, table_dev, positions.to(DEV), q, k, v, ck, cv, rows.to(DEV), H, KV, hd, 1e-5, ws)
+    torch.cuda.synchronize()
+    assert_bf16_close(q, q_ref.reshape(T, -1), what="q")
+    assert_bf16_close(k, k_ref.reshape(T, -1), what="k")
+    assert_bf16_close(v, v_ref, what="v")
+    # scatter: cached rows hold exactly what was written to k/v, everything else untouched (still NaN)
+    for t, r in enumerate(rows.tolist()):
+        if r >= 0:
+            assert torch.equal(ck[r].reshape(-1), k[t]) and torch.equal(cv[r].reshape(-1), v[t])
+    untouched = torch.ones(n_rows, dtype=torch.bool)
+    untouched[[r for r in rows.tolist() if r >= 0]] = False
+    assert torch.isnan(ck[untouched.to(DEV)].float()).all()
+
+
+@pytest.mark.parametrize("T", [1, 3, 4, 7, 130, 300])
+@pytest.mark.parametrize("N,K", [(256, 512), (4096, 4096), (4096, 14336), (8, 256)])
+def test_linear_residual(T, N, K, ws):
+    if K >= 4096 and T not in (1, 4, 130):
+        pytest.skip("big shape: representative T only")
+    x, w, res = rnd(T, K, seed=8), rnd(N, K, seed=9, scale=K ** -0.5), rnd(T, N, seed=10)
+    out = torch.empty(T, N, dtype=torch.bfloat16, device=DEV)
+    _abi.linear_residual(x.to(DEV), w.to(DEV), res.to(DEV), out, ws)
+    assert_bf16_close(out, res + F.linear(x, w), what="linear+residual")
+    _abi.linear_residual(x.to(DEV), w.to(DEV), None, out, ws)
+    assert_bf16_close(out, F.linear(x, w), what="linear")
+
+
+@pytest.mark.parametrize("T", [1, 2, 4, 6, 129])
+@pytest.mark.parametrize("dim,hid", [(256, 512), (4096, 14336)])
+@pytest.mark.parametrize("with_norm", [True, False])
+def test_ffn_gateup(T, dim, hid, with_norm, ws):
+    if dim == 4096 and T not in (1, 129):
+        pytest.skip("big shape: representative T only")
+    x = rnd(T, dim, seed=11)
+    nw = (1 + 0.2 * rnd(dim, seed=12).float()).to(torch.bfloat16)
+    w1, w3 = rnd(hid, dim, seed=13, scale=dim ** -0.5), rnd(hid, dim, seed=14, scale=dim ** -0.5)
+    xin = R.rms_norm(x, nw, 1e-5) if with_norm else x
+    want = F.silu(F.linear(xin, w1)) * F.linear(xin, w3)
+    w13 = torch.stack([w1, w3], 1).reshape(2 * hid, dim).to(DEV)
+    g = torch.empty(T, hid, dtype=torch.bfloat16, device=DEV)
+    _abi.ffn_gateup(x.to(DEV), nw.to(DEV) if with_norm else None, w13, g, 1e-5, ws)
+    # silu goes through exp(): CUDA expf vs the CPU's vectorised exp differ in the last fp32 bit now and then
+    assert_bf16_close(g, want, max_ulp=1, min_exact=0.96, atol=1e-6, what="ffn gate/up")
+
+
+@pytest.mark.parametrize("T", [1, 4, 9])
+def test_lm_head(T, ws):
+    dim, V = 512, 32000
+    x = rnd(T, dim, seed=15)
+    nw = (1 + 0.2 * rnd(dim, seed=16).float()).to(torch.bfloat16)
+    wo = rnd(V, dim, seed=17, scale=dim ** -0.5)
+    logits = torch.empty(T, V, dtype=torch.float32, device=DEV)
+    _abi.lm_head(x.to(DEV), nw.to(DEV), wo.to(DEV), logits, 1e-5, ws)
+    assert_bf16_close(logits, F.linear(R.rms_norm(x, nw, 1e-5), wo).float(), what="lm head")
+
+
+def test_gemm_against_cuda_core_gemm(ws):
+    """Tensor-core GEMM vs the naive CUDA-core GEMM on the GPU at a size the CPU oracle would take long for."""
+    T, N, K = 515, 1536, 4096
+    a, w = rnd(T, K, seed=18).to(DEV), rnd(N, K, seed=19, scale=K ** -0.5).to(DEV)
+    out = torch.empty(T, N, dtype=torch.bfloat16, device=DEV)
+    _abi.linear_residual(a, w, None, out, ws)
+    assert_bf16_close(out, _abi.test_gemm_naive(a, w).to(torch.bfloat16), what="gemm vs naive")
+
+
+def _oracle_decode(q, ck, cv, kv_len, H, KV):
+    rep = H // KV
+    outs = []
+    for b in range(q.shape[0]):
+        n = int(kv_len[b])
+        keys, vals = ck[b, :n].repeat_interleave(rep, dim=1), cv[b, :n].repeat_interleave(rep, dim=1)
+        outs.append(attend_block(q[b].view(1, H, 128), keys, vals, local_causal_allowed(1, n, None)))
+    return torch.cat(outs, 0).view(q.shape[0], H * 128)
+
+
+@pytest.mark.parametrize("B,W,lens,S", [
+    (1, 64, [1], 1), (1, 64, [5], 3), (3, 100, [100, 37, 1], 4), (2, 4096, [4096, 1000], 37), (1, 4096, [4096], 18),
+    (4, 300, [300, 299, 17, 150], 9),
+])
+@pytest.mark.parametrize("H,KV", [(32, 8), (4, 2), (48, 8)])
+def test_attn_decode(B, W, lens, S, H, KV, ws):
+    if (H, KV) != (32, 8) and W == 4096:
+        pytest.skip("long ring: 7B head layout only")
+    q = rnd(B, H * 128, seed=20)
+    ck, cv = rnd(B + 1, W, KV, 128, seed=21), rnd(B + 1, W, KV, 128, seed=22)  # max_batch > B like tests/test_generate.py:212
+    kv_len = torch.tensor(lens, dtype=torch.int32)
+    want = _oracle_decode(q, ck, cv, kv_len, H, KV)
+    ck_d, cv_d = ck.to(DEV), cv.to(DEV)
+    for b, n in enumerate(lens):  # slots >= kv_len are uninitialised memory in the reference (cache.py:166): poison them
+        ck_d[b, n:] = float("nan")
+        cv_d[b, n:] = float("nan")
+    out = torch.empty(B, H * 128, dtype=torch.bfloat16, device=DEV)
+    for _ in range(2):  # twice: the split counters must self-reset
+        out.zero_()
+        _abi.attn_decode(q.to(DEV), ck_d, cv_d, kv_len.to(DEV), out, H, KV, 128, S, ws)
+        assert_bf16_close(out, want, max_ulp=1, min_exact=0.9, atol=2e-3, what="decode attention")
+
+
+def _oracle_prefill(q, k_new, v_new, ck, cv, seqlens, seqpos, W, H, KV):
+    rep = H // KV
+    outs, o = [], 0
+    for b, (s, p) in enumerate(zip(seqlens, seqpos)):
+        old_k, old_v = R._unrotate(ck[b], p), R._unrotate(cv[b], p)
+        keys = torch.cat([old_k, k_new[o:o + s].view(s, KV, 128)], 0).repeat_interleave(rep, dim=1)
+        vals = torch.cat([old_v, v_new[o:o + s].view(s, KV, 128)], 0).repeat_interleave(rep, dim=1)
+        outs.append(attend_block(q[o:o + s].view(s, H, 128), keys, vals, local_causal_allowed(s, keys.shape[0], W)))
+        o += s
+    return torch.cat(outs, 0).view(-1, H * 128)
+
+
+@pytest.mark.parametrize("seqlens,seqpos,W", [
+    ([7, 3, 3, 3], [0, 0, 0, 0], 64),        # first prefill, ragged (tests/test_generate.py:39)
+    ([70, 130], [0, 0], 256),                # several query/key tiles
+    ([70, 130], [0, 0], 33),                 # window smaller than the chunk
+    ([5, 5], [5, 5], 4),                     # chunked prefill, ring already wrapped (W < seen)
+    ([65, 3], [100, 250], 128),              # chunk on top of a wrapped ring, ragged
+    ([1, 9], [40, 3], 16),                   # a one-token sequence inside a prefill batch
+    ([300], [0], 4096),
+])
+@pytest.mark.parametrize("H,KV", [(4, 2), (32, 8)])
+def test_attn_prefill(seqlens, seqpos, W, H, KV):
+    if (H, KV) == (32, 8) and sum(seqlens) > 150:
+        pytest.skip("big head count: small cases only")
+    T, B = sum(seqlens), len(seqlens)
+    q, k_new, v_new = rnd(T, H * 128, seed=23), rnd(T, KV * 128, seed=24), rnd(T, KV * 128, seed=25)
+    ck, cv = torch.zeros(B, W, KV, 128, dtype=torch.bfloat16), torch.zeros(B, W, KV, 128, dtype=torch.bfloat16)
+    valid = torch.zeros(B, W, dtype=torch.bool)
+    g = torch.Generator().manual_seed(26)
+    for b, p in enumerate(seqpos):  # fill the ring as if positions [0, p) had been cached
+        for pos in range(max(0, p - W), p):
+            ck[b, pos % W] = torch.randn(KV, 128, generator=g).to(torch.bfloat16)
+            cv[b, pos % W] = torch.randn(KV, 128, generator=g).to(torch.bfloat16)
+            valid[b, pos % W] = True
+    want = _oracle_prefill(q, k_new, v_new, ck, cv, seqlens, seqpos, W, H, KV)
+    ck_d, cv_d = ck.to(DEV), cv.to(DEV)
+    ck_d[~valid.to(DEV)] = float("nan")  # never-written slots must not be read
+    cv_d[~valid.to(DEV)] = float("nan")
+    q_start = torch.tensor([0] + torch.tensor(seqlens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    out = torch.zeros(T, H * 128, dtype=torch.bfloat16, device=DEV)
+    _abi.attn_prefill(q.to(DEV), k_new.to(DEV), v_new.to(DEV), ck_d, cv_d, q_start, torch.tensor(seqpos, dtype=torch.int32, device=DEV), out,
+                      B, max(seqlens), W, H, KV, 128, causal=True)
+    assert_bf16_close(out, want, max_ulp=2, min_exact=0.5, atol=4e-3, what="prefill attention")
+
+
+def test_attn_prefill_no_cache_unmasked():
+    """cache=None: every query sees every key of the flattened batch."""
+    T, H, KV = 77, 4, 2
+    q, k, v = rnd(T, H * 128, seed=27), rnd(T, KV * 128, seed=28), rnd(T, KV * 128, seed=29)
+    want = attend_block(q.view(T, H, 128), k.view(T, KV, 128).repeat_interleave(2, 1), v.view(T, KV, 128).repeat_interleave(2, 1), None)
+    out = torch.zeros(T, H * 128, dtype=torch.bfloat16, device=DEV)
+    _abi.attn_prefill(q.to(DEV), k.to(DEV), v.to(DEV), None, None, None, None, out, 1, T, 0, H, KV, 128, causal=False)
+    assert_bf16_close(out, want.reshape(T, -1), max_ulp=2, min_exact=0.5, atol=4e-3, what="unmasked attention")
+
+
+def test_kv_ring_write():
+    T, KV = 9, 2
+    k, v = rnd(T, KV * 128, seed=30).to(DEV), rnd(T, KV * 128, seed=31).to(DEV)
+    ck = torch.zeros(16, KV, 128, dtype=torch.bfloat16, device=DEV)
+    cv = torch.zeros_like(ck)
+    rows = torch.tensor([-1, -1, 3, 4, 5, -1, 15, 0, 1], dtype=torch.int32, device=DEV)
+    _abi.kv_ring_write(k, v, ck, cv, rows, KV, 128)
+    for t, r in enumerate(rows.tolist()):
+        if r >= 0:
+            assert torch.equal(ck[r].reshape(-1), k[t]) and torch.equal(cv[r].reshape(-1), v[t])
+    assert ck[[2, 6, 7]].abs().sum() == 0

@@ -53,3 +53,19 @@ def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def same_machine_as_golden(meta: dict) -> bool:
     return meta.get("torch") == torch.__version__ and meta.get("cpu_capability") == torch.backends.cpu.get_cpu_capability()
+
+
+def assert_bf16_close(got: torch.Tensor, want: torch.Tensor, max_ulp: int = 1, min_exact: float = 0.97, atol: float = 0.0, what: str = ""):
+    """Element-wise comparison of two tensors of bf16-rounded values: every element within `max_ulp` bf16 ulps
+    (or `atol` absolute, for values near zero where cancellation makes ulps meaningless) and at least
+    `min_exact` of them bit-identical.  Returns (exact fraction, max ulp) for reporting."""
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite values in output"
+    ulps = bf16_ulp_diff(got, want)
+    ok = (ulps <= max_ulp) | ((got - want).abs() <= atol)
+    exact = (ulps == 0).float().mean().item()
+    worst = int(ulps[~((got - want).abs() <= atol)].max().item()) if (~((got - want).abs() <= atol)).any() else 0
+    assert ok.all(), f"{what}: {(~ok).sum().item()} / {ok.numel()} elements differ by more than {max_ulp} bf16 ulp (worst {worst}); exact={exact:.4f}"
+    assert exact >= min_exact, f"{what}: only {exact:.4f} of elements bit-exact (need {min_exact})"
+    return exact, worst
