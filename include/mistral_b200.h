@@ -132,6 +132,36 @@ int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* l
 size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
                              int64_t hidden, int64_t vocab, int64_t max_batch);
 
+/* ---------------------------------------------------------------------------------------------
+ * One whole decode step (batch 1) as ONE persistent cooperative kernel: embedding row -> n_layers x
+ * [RMSNorm+QKV+RoPE+ring write | GQA attention over the ring | wo+residual | RMSNorm+gate/up+SiLU*mul |
+ * down+residual] -> final RMSNorm + lm head.  Replaces one Transformer.forward(next_token, seqlens=[1], cache)
+ * call of the decode loop (generate.py:139 -> transformer.py:163-242) including every per-layer library call.
+ * Weights stream through a shared-memory ring fed by TMA bulk copies that keep prefetching across the phase
+ * (grid) barriers, which is what lets a batch-1 step approach the HBM roofline.
+ *   layers_dev   [n_layers] mb200_layer_desc in DEVICE memory (pointers to this layer's packed weights + ring)
+ *   windows_dev  [n_layers] int32 ring size W of each layer
+ *   token_dev    device int64 scalar (e.g. the previous step's argmax); pos = its absolute position;
+ *                batch_row = which row of the [max_batch, W, KV, hd] cache this sequence occupies
+ *   logits       [vocab] fp32
+ * Requires a device that can co-schedule one CTA per SM (cooperative launch).
+ */
+typedef struct mb200_layer_desc {
+  const void* wqkv;      /* [(H+2KV)*hd, dim] */
+  const void* wo;        /* [dim, H*hd] */
+  const void* w13;       /* [2*hidden, dim], rows interleaved w1/w3 */
+  const void* w2;        /* [dim, hidden] */
+  const void* attn_norm; /* [dim] */
+  const void* ffn_norm;  /* [dim] */
+  void* cache_k;         /* [max_batch, W, KV, hd] */
+  void* cache_v;
+} mb200_layer_desc;
+
+int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb,
+                      const void* final_norm, const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos,
+                      int64_t batch_row, float* logits, int64_t dim, int64_t hidden, int64_t n_heads, int64_t n_kv_heads,
+                      int64_t head_dim, int64_t vocab, float eps, void* workspace, size_t workspace_bytes, void* stream);
+
 #define MB200_SKINNY_MAX_T 4
 
 /* Workspace contract: the first 64 KiB of `workspace` hold self-resetting counters; the caller zero-fills the

@@ -7,15 +7,5 @@ using the model does -- and fails loudly if it is missing.
 """
 from .args import MoeArgs, TransformerArgs  # noqa: F401
 from .cache import BufferCache  # noqa: F401
-
-
-def __getattr__(name):  # lazy: keep `import mistral_inference_b200.synth` light
-    if name == "Transformer":
-        from .transformer import Transformer
-
-        return Transformer
-    if name == "generate":
-        from .generate import generate
-
-        return generate
-    raise AttributeError(name)
+from .generate import generate  # noqa: F401  (the function; the submodule stays importable as mistral_inference_b200.generate)
+from .transformer import Transformer  # noqa: F401

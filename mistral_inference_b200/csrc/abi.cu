@@ -1,6 +1,7 @@
 // libmb200.so -- the C ABI declared in include/mistral_b200.h.  Argument checking + kernel dispatch only.
 #include "attn_decode.cuh"
 #include "attn_prefill.cuh"
+#include "decode_megakernel.cuh"
 #include "elementwise.cuh"
 #include "gemm_mma.cuh"
 #include "skinny_linear.cuh"
@@ -78,6 +79,10 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
   size_t s = kWsHeader;
   s += align256((size_t)T * widest * 2);                                  // normed activations
   s += attn_decode_workspace(max_batch, n_kv_heads, 64, rep);             // split-KV partials (n_splits <= 64)
+  // decode_step scratch (residual ping-pong, h, q, attn, g) lives in the same region as the normed activations
+  const size_t mk = 6 * 256 + (size_t)(3 * dim + 2 * n_heads * head_dim + hidden) * 2 +
+                    (size_t)n_kv_heads * MK_MAX_SPLITS * rep * (kHeadDim + 2) * sizeof(float) + 256;
+  if (s < kWsHeader + mk) s = kWsHeader + mk;
   return s;
 }
 
@@ -220,6 +225,93 @@ int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* l
   e.out_f32 = logits;
   e.ld_out = vocab;
   return run_linear<EPI_F32>(x, norm_w, w_out, e, T, vocab, dim, eps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb, const void* final_norm,
+                      const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos, int64_t batch_row, float* logits, int64_t dim,
+                      int64_t hidden, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int64_t vocab, float eps, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  static_assert(sizeof(mb200_layer_desc) == sizeof(MkLayer), "layer descriptor layout");
+  MB_CHECK_ARG(layers_dev && windows_dev && emb && final_norm && w_out && rope && token_dev && logits && workspace, "decode_step: null pointer");
+  MB_CHECK_ARG(head_dim == kHeadDim, "decode_step: head_dim=%lld unsupported (128 only)", (long long)head_dim);
+  MB_CHECK_ARG(n_heads % n_kv_heads == 0, "decode_step: H %% KV != 0");
+  const int rep = (int)(n_heads / n_kv_heads);
+  const int64_t q_dim = n_heads * head_dim;
+  auto cut_ok = [](int64_t K) { const int64_t nch = (K + MK_MAX_KC - 1) / MK_MAX_KC; return K % (nch * 8) == 0; };
+  MB_CHECK_ARG(cut_ok(dim) && cut_ok(hidden) && cut_ok(q_dim), "decode_step: dim/hidden/q_dim must split into 16-byte-aligned row chunks");
+  MB_CHECK_ARG(vocab % 2 == 0 && hidden % 1 == 0, "decode_step: vocab must be even");
+  int dev = 0, sms = 0, smem_max = 0, coop = 0;
+  MB_CHECK_CUDA(cudaGetDevice(&dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  MB_CHECK_ARG(coop, "decode_step: device does not support cooperative launch");
+
+  MkParams p;
+  p.layers = reinterpret_cast<const MkLayer*>(layers_dev);
+  p.windows = windows_dev;
+  p.n_layers = (int)n_layers;
+  p.emb = (const bf16*)emb;
+  p.final_norm = (const bf16*)final_norm;
+  p.w_out = (const bf16*)w_out;
+  p.rope = rope;
+  p.token = token_dev;
+  p.pos = (int)pos;
+  p.batch_row = (int)batch_row;
+  p.logits = logits;
+  p.dim = (int)dim;
+  p.hidden = (int)hidden;
+  p.H = (int)n_heads;
+  p.KV = (int)n_kv_heads;
+  p.vocab = (int)vocab;
+  p.eps = eps;
+  // shared memory plan: x buffer (also the attention merge scratch), barriers + reduction scratch, the rest is the ring
+  int64_t widest = dim > hidden ? dim : hidden;
+  if (q_dim > widest) widest = q_dim;
+  size_t xs_bytes = (size_t)widest * 2;
+  const size_t attn_scratch = (size_t)(2 * MK_CONSUMER_WARPS * AD_MAX_REP + MK_CONSUMER_WARPS * AD_MAX_REP * kHeadDim) * sizeof(float);
+  if (xs_bytes < attn_scratch) xs_bytes = attn_scratch;
+  xs_bytes = (xs_bytes + 127) & ~(size_t)127;
+  const size_t tail = 2 * MK_MAX_STAGES * sizeof(uint64_t) + (8 + 32 + 4) * sizeof(float) + 64;
+  int n_stages = (int)(((size_t)smem_max - xs_bytes - tail) / MK_STAGE_BYTES);
+  if (n_stages > MK_MAX_STAGES) n_stages = MK_MAX_STAGES;
+  MB_CHECK_ARG(n_stages >= 3, "decode_step: not enough shared memory for the weight ring (%d stages)", n_stages);
+  p.n_stages = n_stages;
+  p.xs_bytes = (int)xs_bytes;
+  const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
+
+  // global scratch: header words + activations + split-KV partials
+  int S = sms / (int)n_kv_heads;
+  if (S < 1) S = 1;
+  if (S > MK_MAX_SPLITS) S = MK_MAX_SPLITS;
+  uint8_t* ws = (uint8_t*)workspace;
+  p.bar_count = (unsigned*)(ws + 4096);
+  p.bar_gen = (unsigned*)(ws + 4096 + 256);
+  p.attn_counters = (int*)(ws + 8192);
+  MB_CHECK_ARG((size_t)n_kv_heads * sizeof(int) <= 4096, "decode_step: too many kv heads");
+  size_t off = kWsHeader;
+  auto take = [&](size_t bytes) { uint8_t* r = ws + off; off += align256(bytes); return r; };
+  p.xbuf = (bf16*)take((size_t)2 * dim * 2);
+  p.hbuf = (bf16*)take((size_t)dim * 2);
+  p.qbuf = (bf16*)take((size_t)q_dim * 2);
+  p.abuf = (bf16*)take((size_t)q_dim * 2);
+  p.gbuf = (bf16*)take((size_t)hidden * 2);
+  p.partial = (float*)take((size_t)n_kv_heads * S * rep * (kHeadDim + 2) * sizeof(float));
+  if (workspace_bytes < off) return fail(MB200_E_WORKSPACE, "decode_step: workspace %zu < %zu", workspace_bytes, off);
+
+  void* args[] = {(void*)&p};
+  const void* fn = nullptr;
+  switch (rep) {
+    case 1: fn = (const void*)decode_megakernel<1>; break;
+    case 2: fn = (const void*)decode_megakernel<2>; break;
+    case 4: fn = (const void*)decode_megakernel<4>; break;
+    case 6: fn = (const void*)decode_megakernel<6>; break;
+    case 8: fn = (const void*)decode_megakernel<8>; break;
+    default: return fail(MB200_E_INVALID, "decode_step: H/KV=%d unsupported (1,2,4,6,8)", rep);
+  }
+  MB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sms), dim3(MK_THREADS), args, smem, (cudaStream_t)stream));
+  return MB200_OK;
 }
 
 // Test-only: CUDA-core fp32-accumulate GEMM (c fp32 [T, N]) used to cross-check the tensor-core kernels on the GPU.

@@ -209,12 +209,50 @@ class Transformer(nn.Module):
         host = cache._kv_seqlens_host
         return host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
 
+    def _megakernel_ok(self, B: int) -> bool:
+        return B == 1 and self.args.moe is None and self.num_pipeline_ranks == 1 and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
+
+    def _decode_megakernel(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
+        """Batch-1 decode step as ONE persistent cooperative kernel (csrc/decode_megakernel.cuh)."""
+        import numpy as np
+
+        a = self.args
+        key = ("mk", id(cache))
+        st = self._decode_graphs.get(key)
+        ws = self.workspace(1)
+        if st is None or st["cache"] is not cache:
+            blocks = list(self.layers.values())
+            desc = np.zeros((len(blocks), 8), dtype=np.uint64)
+            for i, blk in enumerate(blocks):
+                ff = blk.feed_forward
+                desc[i] = [blk.attention.wqkv.data_ptr(), blk.attention.wo_weight.data_ptr(), ff.w13.data_ptr(), ff.w2_weight.data_ptr(),
+                           blk.attention_norm.weight.data_ptr(), blk.ffn_norm.weight.data_ptr(), cache.cache_k[i].data_ptr(),
+                           cache.cache_v[i].data_ptr()]
+            st = {"cache": cache,
+                  "layers": torch.from_numpy(desc.view(np.int64)).to(self.device),
+                  "windows": torch.tensor(cache.cache_sizes, dtype=torch.int32, device=self.device),
+                  "token": torch.zeros(1, dtype=torch.long, device=self.device),
+                  "logits": torch.empty(1, self.vocab_size, dtype=torch.float32, device=self.device)}
+            self._decode_graphs[key] = st
+        if cache._kv_seqlens_host is None:
+            cache.init_kvseqlens(1)
+        pos = cache._kv_seqlens_host[0]
+        assert pos < self.rope_table.shape[0]
+        st["token"].copy_(tokens.reshape(1), non_blocking=True)
+        _abi.decode_step(st["layers"], st["windows"], self.n_local_layers, self.tok_embeddings.weight, self.norm.weight, self.output_weight,
+                         self.rope_table, st["token"], pos, 0, st["logits"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
+                         self.vocab_size, a.norm_eps, ws)
+        cache.update_seqlens([1])
+        return st["logits"]
+
     def decode_static(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
         """One decode step for every sequence of `cache` (one new token each) replayed from a CUDA graph: the ~5
         kernels per layer are enqueued with a single graph launch instead of ~165 Python->C calls.  Returns the
         graph's STATIC fp32 logits buffer [B, V] (overwritten by the next step).  The first call per
         (cache, batch) runs eagerly (warm-up), the second captures."""
         B = tokens.shape[0]
+        if self._megakernel_ok(B):
+            return self._decode_megakernel(tokens, cache)
         seqlens = [1] * B
         key = (id(cache), B)
         self.workspace(B)

@@ -24,13 +24,13 @@ for s in $STEPS; do
       echo "bench exit $?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
       ;;
     launches)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
-        python bench.py --steps 2 --warmup 3 --prefill 1024 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
+      MB200_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 4 --warmup 3 --prefill 4096 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
       echo "launches exit $?"; wc -l gpurun_out/launches.csv
       ;;
     ncu:*)
       pat="${s#ncu:}"
-      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${pat}" -s 40 -c 3 -f -o "gpurun_out/prof_${pat//[^a-zA-Z0-9_]/_}" \
+      MB200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:${pat}" -s 40 -c 6 -f -o "gpurun_out/prof_${pat//[^a-zA-Z0-9_]/_}" \
         python bench.py --steps 2 --warmup 3 --prefill 512 --layers 8 --no-cpu-baseline > "gpurun_out/ncu_${pat//[^a-zA-Z0-9_]/_}.log" 2>&1
       echo "ncu $pat exit $?"
       ;;

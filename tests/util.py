@@ -55,11 +55,14 @@ def same_machine_as_golden(meta: dict) -> bool:
     return meta.get("torch") == torch.__version__ and meta.get("cpu_capability") == torch.backends.cpu.get_cpu_capability()
 
 
-def assert_bf16_close(got: torch.Tensor, want: torch.Tensor, max_ulp: int = 1, min_exact: float = 0.97, atol: float = 0.0, what: str = ""):
+def assert_bf16_close(got: torch.Tensor, want: torch.Tensor, max_ulp: int = 1, min_exact: float = 0.97, atol: float = None, what: str = ""):
     """Element-wise comparison of two tensors of bf16-rounded values: every element within `max_ulp` bf16 ulps
     (or `atol` absolute, for values near zero where cancellation makes ulps meaningless) and at least
-    `min_exact` of them bit-identical.  Returns (exact fraction, max ulp) for reporting."""
+    `min_exact` of them bit-identical.  Default atol = 1e-5 * max(1, max|want|): the fp32 accumulation-order
+    noise of a K~4k..14k dot product (this is the north-star's atol=1e-5).  Returns (exact fraction, max ulp)."""
     got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    if atol is None:
+        atol = 1e-5 * max(1.0, want.abs().max().item())
     assert got.shape == want.shape, (got.shape, want.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite values in output"
     ulps = bf16_ulp_diff(got, want)
