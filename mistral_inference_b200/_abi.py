@@ -40,6 +40,7 @@ _SIGNATURES = {
     "mb200_workspace_bytes": (c_size_t, [c_int64] * 8),
     "mb200_decode_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
+    "mb200_debug_set_decode_timeline": (c_int, [c_void_p]),
     "mb200_test_gemm_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
 }
 
@@ -175,6 +176,10 @@ def decode_step(layers_dev, windows_dev, n_layers, emb, final_norm, w_out, rope,
     _check(lib().mb200_decode_step(_ptr(layers_dev), _ptr(windows_dev), n_layers, _ptr(emb), _ptr(final_norm), _ptr(w_out), _ptr(rope),
                                    _ptr(token_dev), pos, batch_row, _ptr(logits), dim, hidden, n_heads, n_kv_heads, head_dim, vocab, eps,
                                    ws.ptr, ws.nbytes, _stream()), "mb200_decode_step")
+
+
+def set_decode_timeline(buf: Optional[torch.Tensor]) -> None:
+    _check(lib().mb200_debug_set_decode_timeline(_ptr(buf)), "mb200_debug_set_decode_timeline")
 
 
 def test_gemm_naive(a, w) -> torch.Tensor:

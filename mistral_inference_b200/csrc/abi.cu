@@ -8,6 +8,7 @@
 
 namespace mb200 {
 thread_local char g_err[512] = "";
+static unsigned long long* g_mk_prof = nullptr;  // debug: decode megakernel phase timeline buffer (device)
 
 constexpr size_t kWsHeader = 64 * 1024;  // persistent, zero-initialised by the caller once: self-resetting counters
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -275,7 +276,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   const size_t tail = 2 * MK_MAX_STAGES * sizeof(uint64_t) + (8 + 32 + 4) * sizeof(float) + 64;
   int n_stages = (int)(((size_t)smem_max - xs_bytes - tail) / MK_STAGE_BYTES);
   if (n_stages > MK_MAX_STAGES) n_stages = MK_MAX_STAGES;
-  MB_CHECK_ARG(n_stages >= 3, "decode_step: not enough shared memory for the weight ring (%d stages)", n_stages);
+  MB_CHECK_ARG(n_stages > MK_CONSUMER_WARPS, "decode_step: not enough shared memory for the weight ring (%d stages)", n_stages);
   p.n_stages = n_stages;
   p.xs_bytes = (int)xs_bytes;
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
@@ -297,6 +298,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.abuf = (bf16*)take((size_t)q_dim * 2);
   p.gbuf = (bf16*)take((size_t)hidden * 2);
   p.partial = (float*)take((size_t)n_kv_heads * S * rep * (kHeadDim + 2) * sizeof(float));
+  p.prof = g_mk_prof;
   if (workspace_bytes < off) return fail(MB200_E_WORKSPACE, "decode_step: workspace %zu < %zu", workspace_bytes, off);
 
   void* args[] = {(void*)&p};
@@ -311,6 +313,12 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   }
   MB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sms), dim3(MK_THREADS), args, smem, (cudaStream_t)stream));
+  return MB200_OK;
+}
+
+// Debug: device buffer of n_layers*12 uint64 that CTA 0 of the decode megakernel fills with %globaltimer stamps (NULL = off).
+int mb200_debug_set_decode_timeline(void* device_buffer) {
+  g_mk_prof = (unsigned long long*)device_buffer;
   return MB200_OK;
 }
 

@@ -69,7 +69,16 @@ struct MkParams {
   bf16* abuf;           // [H*hd] attention output
   bf16* gbuf;           // [hidden]
   float* partial;       // [KV][splits][REP][hd+2]
+  unsigned long long* prof;  // optional [n_layers][12] globaltimer stamps written by CTA 0 (debug timeline), or null
 };
+
+__device__ __forceinline__ void mk_stamp(const MkParams& p, int tid, int layer, int idx) {
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.prof[layer * 12 + idx] = t;
+  }
+}
 
 // ---- PTX: mbarrier + bulk copy ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,85 +156,92 @@ struct RingState {
   uint32_t it;  // running stage counter (same sequence in producer and consumers)
 };
 
+// Stage order inside a matrix (same in producer and consumers): the CTA's pairs are taken in GROUPS of up to 8 (one pair
+// per consumer warp); inside a group the stages are chunk-major: (pair g0+0, ch 0) ... (pair g0+g-1, ch 0), (pair g0+0, ch 1) ...
+// So warp w touches stages base + ch*g + w: never more than 8 apart, i.e. always within one lap of the (>= 9-stage) ring --
+// which is what makes parity-based mbarrier waits safe (a waiter two laps ahead would alias and pass early).
+
 // ---- producer: stream this CTA's slice of one matrix --------------------------------------------
 __device__ __forceinline__ void produce_matrix(const bf16* W, int N, int K, uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages,
                                                RingState& rs) {
   const MatCut c = cut_matrix(N, K);
   const uint32_t row_bytes = (uint32_t)c.kc * 2;
-  for (int pair = c.p0; pair < c.p1; ++pair) {
-    const bf16* r0 = W + (int64_t)(2 * pair) * K;
+  for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
+    const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
     for (int ch = 0; ch < c.nch; ++ch) {
-      const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
-      mbar_wait(&empty[slot], par ^ 1);
-      uint8_t* dst = ring + (size_t)slot * MK_STAGE_BYTES;
-      mbar_arrive_expect_tx(&full[slot], 2 * row_bytes);
-      if (c.nch == 1) {
-        bulk_g2s(dst, r0, 2 * row_bytes, &full[slot]);  // the two rows are contiguous
-      } else {
-        bulk_g2s(dst, r0 + ch * c.kc, row_bytes, &full[slot]);
-        bulk_g2s(dst + row_bytes, r0 + K + ch * c.kc, row_bytes, &full[slot]);
+      for (int w = 0; w < g; ++w) {
+        const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
+        const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
+        mbar_wait(&empty[slot], par ^ 1);
+        uint8_t* dst = ring + (size_t)slot * MK_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[slot], 2 * row_bytes);
+        if (c.nch == 1) {
+          bulk_g2s(dst, r0, 2 * row_bytes, &full[slot]);  // the two rows are contiguous
+        } else {
+          bulk_g2s(dst, r0 + ch * c.kc, row_bytes, &full[slot]);
+          bulk_g2s(dst + row_bytes, r0 + K + ch * c.kc, row_bytes, &full[slot]);
+        }
+        ++rs.it;
       }
-      ++rs.it;
     }
   }
 }
 
 // ---- consumers: y[pair] = W[pair rows] . xs, epilogue(pair, acc0, acc1) on one lane ----------------
+// Warp-per-pair inside a group: warp w owns pair g0+w and consumes its `nch` stages by itself (32 lanes x 16 B per step,
+// unrolled -> plenty of ILP); only the owning warp releases a slot (empty barriers have arrival count 1).  One block
+// barrier per GROUP keeps all warps within a group of each other (see the stage-order note above).
 template <class Epi>
 __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages, RingState& rs,
-                                               const uint4* xs, float (*part)[MK_CONSUMER_WARPS][2], int tid, Epi epi) {
+                                               const uint4* xs, int tid, Epi epi) {
   const MatCut c = cut_matrix(N, K);
   const int lane = tid & 31, warp = tid >> 5;
   const int kc8 = c.kc >> 3;  // 16-byte chunks per row chunk
-  for (int pair = c.p0; pair < c.p1; ++pair) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int ch = 0; ch < c.nch; ++ch) {
-      const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
-      mbar_wait(&full[slot], par);
-      const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
-      const uint4* w1 = w0 + kc8;
-      const uint4* xc = xs + ch * kc8;
-#pragma unroll 2
-      for (int i = tid; i < kc8; i += MK_CONSUMERS) {
-        const uint4 a = w0[i], b = w1[i], x = xc[i];
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
+  for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
+    const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
+    if (warp < g) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int ch = 0; ch < c.nch; ++ch) {
+        const uint32_t it = rs.it + (uint32_t)(ch * g + warp);
+        const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
+        // Guard (tests/test_megakernel_protocol.py): bulk copies land out of order, so this warp may get here before the
+        // slot's PREVIOUS fill (owned by another warp) has landed; `full` would then still be one phase behind and a
+        // parity wait would alias and pass early.  Waiting first until that previous fill has been CONSUMED (same
+        // condition the producer waits for before refilling) pins `full` to phase {r, r+1} when it is tested.
+        mbar_wait(&empty[slot], par ^ 1);
+        mbar_wait(&full[slot], par);
+        const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
+        const uint4* w1 = w0 + kc8;
+        const uint4* xc = xs + ch * kc8;
+#pragma unroll 4
+        for (int i = lane; i < kc8; i += 32) {
+          const uint4 a = w0[i], b = w1[i], x = xc[i];
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
-          a0 = fmaf(bf16lo(aw[j]), xl, a0);
-          a0 = fmaf(bf16hi(aw[j]), xh, a0);
-          a1 = fmaf(bf16lo(bw[j]), xl, a1);
-          a1 = fmaf(bf16hi(bw[j]), xh, a1);
+          for (int j = 0; j < 4; ++j) {
+            const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
+            a0 = fmaf(bf16lo(aw[j]), xl, a0);
+            a0 = fmaf(bf16hi(aw[j]), xh, a0);
+            a1 = fmaf(bf16lo(bw[j]), xl, a1);
+            a1 = fmaf(bf16hi(bw[j]), xh, a1);
+          }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is the only reader of the slot
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is done reading the slot
-      ++rs.it;
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane == 0) epi(2 * (g0 + warp), a0, a1);
     }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    const int pb = pair & 1;
-    if (lane == 0) {
-      part[pb][warp][0] = a0;
-      part[pb][warp][1] = a1;
-    }
+    rs.it += (uint32_t)(g * c.nch);
     consumer_sync();
-    if (warp == (pair & (MK_CONSUMER_WARPS - 1))) {  // finisher warp of this pair; the others move on
-      float v0 = lane < MK_CONSUMER_WARPS ? part[pb][lane][0] : 0.f;
-      float v1 = lane < MK_CONSUMER_WARPS ? part[pb][lane][1] : 0.f;
-#pragma unroll
-      for (int o = MK_CONSUMER_WARPS / 2; o > 0; o >>= 1) {
-        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-      }
-      if (lane == 0) epi(2 * pair, v0, v1);
-    }
   }
 }
 
 // ---- consumers: stage an activation vector (written by other CTAs: L2 loads) and optionally RMS-normalise it ----
 __device__ __forceinline__ void stage_x(uint4* xs, const bf16* src, const bf16* norm_w, int K, float eps, float* red, int tid) {
   const int kc = K >> 3;
+#pragma unroll 4
   for (int i = tid; i < kc; i += MK_CONSUMERS) xs[i] = ldcg16(reinterpret_cast<const uint4*>(src) + i);
   consumer_sync();
   if (norm_w == nullptr) return;
@@ -300,7 +316,7 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
   const bf16* kbase = L.cache_k + ((int64_t)p.batch_row * W) * row_stride + (int64_t)g * kHeadDim + hl * 8;
   const bf16* vbase = L.cache_v + ((int64_t)p.batch_row * W) * row_stride + (int64_t)g * kHeadDim + hl * 8;
   constexpr int STRIDE = MK_CONSUMER_WARPS * 2;
-  constexpr int PF = 2;  // key pairs in flight per half-warp beyond the current one
+  constexpr int PF = 5;  // keys in flight per half-warp beyond the current one (16 half-warps x 5 x 512 B = 40 KB per SM)
   int slot = k_begin + warp * 2 + half;
   uint4 kq[PF], vq[PF];
 #pragma unroll
@@ -446,7 +462,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + p.xs_bytes);
   uint64_t* empty = full + MK_MAX_STAGES;
   float* red = reinterpret_cast<float*>(empty + MK_MAX_STAGES);                       // [8]
-  float(*part)[MK_CONSUMER_WARPS][2] = reinterpret_cast<float(*)[MK_CONSUMER_WARPS][2]>(red + 8);  // [2][8][2]
   int* sm_flag = reinterpret_cast<int*>(red + 8 + 32);
   // attention merge scratch aliases the xs buffer (xs is dead during phase 2): m, l [8*REP], acc [8*REP*128]
   float* sm_m = reinterpret_cast<float*>(xs);
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], MK_CONSUMER_WARPS);
+      mbar_init(&empty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -491,13 +506,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     bf16* x_out = p.xbuf + (size_t)((l + 1) & 1) * p.dim;
 
     // ---- phase 1: RMSNorm + QKV + RoPE + ring scatter ----
+    mk_stamp(p, tid, l, 0);
     stage_x(xs, x_in, L.attn_norm, p.dim, p.eps, red, tid);
+    mk_stamp(p, tid, l, 1);
     {
       const int slot_row = p.batch_row * W + p.pos % W;
       const float* rope_row = p.rope + (int64_t)p.pos * (kHeadDim / 2) * 2;
       bf16* ck = L.cache_k + (int64_t)slot_row * kv_dim;
       bf16* cv = L.cache_v + (int64_t)slot_row * kv_dim;
-      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, part, tid, [&](int n, float a0, float a1) {
+      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n, float a0, float a1) {
         const float y0 = round_bf16(a0), y1 = round_bf16(a1);
         if (n < q_dim + kv_dim) {
           const float2 cs = *reinterpret_cast<const float2*>(rope_row + ((n & (kHeadDim - 1)) >> 1) * 2);
@@ -513,40 +530,50 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
         }
       });
     }
+    mk_stamp(p, tid, l, 2);
     grid_barrier(p, tid);
+    mk_stamp(p, tid, l, 3);
 
     // ---- phase 2: attention over the ring ----
     mk_attention<REP>(p, L, W, tid, sm_m, sm_l, sm_acc, sm_flag);
+    mk_stamp(p, tid, l, 4);
     grid_barrier(p, tid);
+    mk_stamp(p, tid, l, 5);
 
     // ---- phase 3: wo + residual ----
     stage_x(xs, p.abuf, nullptr, q_dim, 0.f, red, tid);
-    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, part, tid, [&](int n, float a0, float a1) {
+    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n, float a0, float a1) {
       const uint32_t r = ldcg_u32(x_in + n);
       *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
+    mk_stamp(p, tid, l, 6);
     grid_barrier(p, tid);
+    mk_stamp(p, tid, l, 7);
 
     // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
     stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-    consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, part, tid, [&](int n, float a0, float a1) {
+    consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n, float a0, float a1) {
       const float s = round_bf16(ref_silu(round_bf16(a0)));
       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
     });
+    mk_stamp(p, tid, l, 8);
     grid_barrier(p, tid);
+    mk_stamp(p, tid, l, 9);
 
     // ---- phase 5: down + residual ----
     stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
-    consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, part, tid, [&](int n, float a0, float a1) {
+    consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n, float a0, float a1) {
       const uint32_t r = ldcg_u32(p.hbuf + n);
       *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
+    mk_stamp(p, tid, l, 10);
     grid_barrier(p, tid);
+    mk_stamp(p, tid, l, 11);
   }
 
   // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) ----
   stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
-  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, part, tid, [&](int n, float a0, float a1) {
+  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n, float a0, float a1) {
     *reinterpret_cast<float2*>(p.logits + n) = make_float2(round_bf16(a0), round_bf16(a1));
   });
 }
