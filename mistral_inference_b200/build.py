@@ -22,12 +22,16 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defines():
+    return [f"-D{d}" for d in os.environ.get("MB200_DEFINES", "").split() if d]
+
+
 def _sources_digest() -> str:
     h = hashlib.sha256()
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "mistral_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_defines()).encode())
     return h.hexdigest()
 
 
@@ -36,7 +40,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-o", str(LIB)] + [str(f) for f in sorted(CSRC.glob("*.cu"))]
+    cmd = [nvcc, *NVCC_FLAGS, *_extra_defines(), "-Xptxas", "-v", "-o", str(LIB)] + [str(f) for f in sorted(CSRC.glob("*.cu"))]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     (CSRC / "ptxas.log").write_text(proc.stderr)
     if proc.returncode != 0:

@@ -82,7 +82,7 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
   s += attn_decode_workspace(max_batch, n_kv_heads, 64, rep);             // split-KV partials (n_splits <= 64)
   // decode_step scratch (residual ping-pong, h, q, attn, g) lives in the same region as the normed activations
   const size_t mk = 6 * 256 + (size_t)(3 * dim + 2 * n_heads * head_dim + hidden) * 2 +
-                    (size_t)n_kv_heads * MK_MAX_SPLITS * rep * (kHeadDim + 2) * sizeof(float) + 256;
+                    (size_t)256 * n_heads * (kHeadDim + 2) * sizeof(float) + 256;  // up to 256 SMs worth of attention slices
   if (s < kWsHeader + mk) s = kWsHeader + mk;
   return s;
 }
@@ -132,7 +132,7 @@ int mb200_attn_decode(const void* q, const void* cache_k, const void* cache_v, c
   MB_CHECK_ARG(n_heads % n_kv_heads == 0, "attn_decode: H %% KV != 0");
   const int rep = (int)(n_heads / n_kv_heads);
   MB_CHECK_ARG(n_splits >= 1 && n_splits <= 64, "attn_decode: n_splits=%lld out of [1, 64]", (long long)n_splits);
-  MB_CHECK_ARG((size_t)B * n_kv_heads * sizeof(int) <= kWsHeader, "attn_decode: B*KV too large for the counter block");
+  MB_CHECK_ARG((size_t)B * n_kv_heads * sizeof(int) <= 8192, "attn_decode: B*KV too large for the counter block");
   AttnDecodeParams p;
   p.q = (const bf16*)q;
   p.cache_k = (const bf16*)cache_k;
@@ -270,8 +270,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   int64_t widest = dim > hidden ? dim : hidden;
   if (q_dim > widest) widest = q_dim;
   size_t xs_bytes = (size_t)widest * 2;
-  const size_t attn_scratch = (size_t)(2 * MK_CONSUMER_WARPS * AD_MAX_REP + MK_CONSUMER_WARPS * AD_MAX_REP * kHeadDim) * sizeof(float);
-  if (xs_bytes < attn_scratch) xs_bytes = attn_scratch;
+  if (xs_bytes < 2048) xs_bytes = 2048;  // also the slice-merge scratch of phase 2b
   xs_bytes = (xs_bytes + 127) & ~(size_t)127;
   const size_t tail = 2 * MK_MAX_STAGES * sizeof(uint64_t) + (8 + 32 + 4) * sizeof(float) + 64;
   int n_stages = (int)(((size_t)smem_max - xs_bytes - tail) / MK_STAGE_BYTES);
@@ -281,14 +280,13 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.xs_bytes = (int)xs_bytes;
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
 
-  // global scratch: header words + activations + split-KV partials
-  int S = sms / (int)n_kv_heads;
-  if (S < 1) S = 1;
-  if (S > MK_MAX_SPLITS) S = MK_MAX_SPLITS;
+  MB_CHECK_ARG(n_kv_heads <= MK_CONSUMER_WARPS, "decode_step: n_kv_heads=%lld > %d (one consumer warp per kv head)", (long long)n_kv_heads,
+               MK_CONSUMER_WARPS);
+  // global scratch: header words + activations + per-slice attention partials
   uint8_t* ws = (uint8_t*)workspace;
-  p.bar_count = (unsigned*)(ws + 4096);
-  p.bar_gen = (unsigned*)(ws + 4096 + 256);
   p.attn_counters = (int*)(ws + 8192);
+  p.bar_flags = (unsigned*)(ws + 16384);  // sms x 32 B
+  MB_CHECK_ARG((size_t)sms * 32 <= kWsHeader - 16384, "decode_step: too many SMs for the barrier flag block");
   MB_CHECK_ARG((size_t)n_kv_heads * sizeof(int) <= 4096, "decode_step: too many kv heads");
   size_t off = kWsHeader;
   auto take = [&](size_t bytes) { uint8_t* r = ws + off; off += align256(bytes); return r; };
@@ -297,7 +295,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.qbuf = (bf16*)take((size_t)q_dim * 2);
   p.abuf = (bf16*)take((size_t)q_dim * 2);
   p.gbuf = (bf16*)take((size_t)hidden * 2);
-  p.partial = (float*)take((size_t)n_kv_heads * S * rep * (kHeadDim + 2) * sizeof(float));
+  p.partial = (float*)take((size_t)sms * n_heads * (kHeadDim + 2) * sizeof(float));  // [slice = CTA][H][m, l, acc[128]]
   p.prof = g_mk_prof;
   if (workspace_bytes < off) return fail(MB200_E_WORKSPACE, "decode_step: workspace %zu < %zu", workspace_bytes, off);
 

@@ -54,10 +54,11 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AttnDecod
       qf[r][2 * j + 1] = bf16hi(u[j]);
     }
   }
+  constexpr float kMasked = -1.0e30f;  // finite "minus infinity" keeps the update branch-free (see the loop below)
   float m[REP], l[REP], acc[REP][8];
 #pragma unroll
   for (int r = 0; r < REP; ++r) {
-    m[r] = -INFINITY;
+    m[r] = kMasked;
     l[r] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
@@ -105,16 +106,17 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AttnDecod
       d += __shfl_xor_sync(0xffffffffu, d, 4);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (valid) {
-        const float sc = d * p.scale;
-        const float mn = fmaxf(m[r], sc);
-        const float corr = exp2f((m[r] - mn) * kLog2e);  // exp2f(-inf) = 0 on the first key
-        const float pr = exp2f((sc - mn) * kLog2e);
-        l[r] = l[r] * corr + pr;
+      // branch-free: a branch here fences each head's FFMA -> shuffle -> exp chain into its own reconvergence region
+      // and serialises the heads (measured 1500 cycles per key pair); as selects the chains interleave
+      const float sc = valid ? d * p.scale : kMasked;
+      const float mn = fmaxf(m[r], sc);
+      const float corr = exp2f((m[r] - mn) * kLog2e);
+      const float pe = exp2f((sc - mn) * kLog2e);
+      const float pr = valid ? pe : 0.f;
+      l[r] = l[r] * corr + pr;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(pr, vf[j], acc[r][j] * corr);
-        m[r] = mn;
-      }
+      for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(pr, vf[j], acc[r][j] * corr);
+      m[r] = mn;
     }
     slot = nslot;
   }
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AttnDecod
     const float mo = __shfl_xor_sync(0xffffffffu, m[r], 16);
     const float lo = __shfl_xor_sync(0xffffffffu, l[r], 16);
     const float mn = fmaxf(m[r], mo);
-    const float cs = (m[r] == -INFINITY) ? 0.f : exp2f((m[r] - mn) * kLog2e);
-    const float co = (mo == -INFINITY) ? 0.f : exp2f((mo - mn) * kLog2e);
+    const float cs = exp2f((m[r] - mn) * kLog2e);  // both empty: 1 * (l = 0)
+    const float co = exp2f((mo - mn) * kLog2e);
     l[r] = l[r] * cs + lo * co;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -195,18 +197,26 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AttnDecod
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // combine: every load independent (see decode_megakernel.cuh): (m, l) of all splits -> shared memory, then one
+  // (head, dim) output per thread with the split loop unrolled
   const float* all = p.partial + (((int64_t)b * p.KV + g) * p.S) * REP * PSTRIDE;
+  __shared__ float cm[64 * REP], cl[64 * REP];
+  for (int i = tid; i < p.S * REP; i += AD_THREADS) {
+    cm[i] = __ldcg(all + (int64_t)i * PSTRIDE);
+    cl[i] = __ldcg(all + (int64_t)i * PSTRIDE + 1);
+  }
+  __syncthreads();
 #pragma unroll
   for (int r = 0; r < REP; ++r) {
     float mn = -INFINITY;
-    for (int t = 0; t < p.S; ++t) mn = fmaxf(mn, __ldcg(all + ((int64_t)t * REP + r) * PSTRIDE));
+    for (int t = 0; t < p.S; ++t) mn = fmaxf(mn, cm[t * REP + r]);
     float lt = 0.f, at = 0.f;
+#pragma unroll 8
     for (int t = 0; t < p.S; ++t) {
-      const float* pp = all + ((int64_t)t * REP + r) * PSTRIDE;
-      const float mt = __ldcg(pp);
+      const float mt = cm[t * REP + r];
       const float c = (mt == -INFINITY) ? 0.f : exp2f((mt - mn) * kLog2e);
-      lt += __ldcg(pp + 1) * c;
-      at += __ldcg(pp + 2 + d) * c;
+      lt += cl[t * REP + r] * c;
+      at += __ldcg(all + ((int64_t)t * REP + r) * PSTRIDE + 2 + d) * c;
     }
     p.out[((int64_t)b * p.H + g * REP + r) * kHeadDim + d] = __float2bfloat16_rn(at / lt);
   }

@@ -17,8 +17,12 @@
 // Row pairs (2 rows = one RoPE pair / one gate-up pair) are dealt to CTAs as contiguous ranges:
 // CTA c owns pairs [c*P/G, (c+1)*P/G) of each matrix, so its slice of every weight matrix is one contiguous byte
 // range and load imbalance is at most one pair.
-// Attention (phase 2) is flash-decoding over the ring with (kv head, split) work items, read directly from
-// global memory by the consumers while the producer is already prefetching the wo slice.
+// Attention (phases 2a/2b) is flash-decoding split by POSITION: CTA c owns ring slots [c*C, (c+1)*C) of the sequence for ALL
+// kv heads, which is one contiguous byte range of the [W, KV, hd] ring for K and one for V -- so it streams through the same
+// shared-memory ring as the weights (large bulk copies, issued by the producer long before phase 1 ends; DRAM-friendly, unlike
+// per-head 256-byte rows at a 2 KB stride).  Warp w serves kv head w (its H/KV query heads) over the slice, so no cross-warp merge
+// is needed; every slice publishes (m, l, acc) per head and phase 2b merges the slices with all loads in flight at once.
+// Only the row of the token being decoded (written in phase 1 by other CTAs) is read from global memory after the barrier.
 #pragma once
 #include "attn_decode.cuh"
 #include "common.cuh"
@@ -60,8 +64,7 @@ struct MkParams {
   float eps;
   int n_stages, xs_bytes;
   // scratch (global)
-  unsigned* bar_count;  // grid barrier arrival counter (self-resetting)
-  unsigned* bar_gen;    // grid barrier generation
+  unsigned* bar_flags;  // grid barrier: one epoch word per CTA, 32-byte stride (persist across launches)
   int* attn_counters;   // [KV]
   bf16* xbuf;           // [2][dim] residual stream ping-pong
   bf16* hbuf;           // [dim]
@@ -72,11 +75,12 @@ struct MkParams {
   unsigned long long* prof;  // optional [n_layers][12] globaltimer stamps written by CTA 0 (debug timeline), or null
 };
 
+// debug timeline: 8 sampled CTAs (every 21st) record %globaltimer at each phase boundary: prof[sample][layer][16] (12..15: inside attention)
 __device__ __forceinline__ void mk_stamp(const MkParams& p, int tid, int layer, int idx) {
-  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) {
+  if (p.prof != nullptr && tid == 0 && blockIdx.x % 21 == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    p.prof[layer * 12 + idx] = t;
+    p.prof[((blockIdx.x / 21) * p.n_layers + layer) * 16 + idx] = t;
   }
 }
 
@@ -88,21 +92,39 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Watchdog: a protocol bug in a persistent cooperative kernel is a GPU hang; every spin loop therefore gives up after
+// ~seconds, prints what it was waiting for and traps, which turns the hang into a reportable launch failure.
+#ifndef MB200_WATCHDOG_SPINS
+#define MB200_WATCHDOG_SPINS (1u << 22)
+#endif
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, uint32_t it = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == MB200_WATCHDOG_SPINS) {
+      printf("[mb200 watchdog] block %d thread %d stuck in mbarrier wait tag=%d it=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x, tag, it,
+             parity);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
@@ -118,22 +140,29 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-// Sense-reversing grid barrier among the consumer threads of all CTAs (self-resetting: usable across launches).
-__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid) {
-  consumer_sync();
-  if (tid == 0) {
-    const unsigned gen = ld_acquire_u32(p.bar_gen);
-    __threadfence();
-    const unsigned arrived = atomicAdd(p.bar_count, 1u);
-    if (arrived == gridDim.x - 1) {
-      atomicExch(p.bar_count, 0u);
-      __threadfence();
-      atomicAdd(p.bar_gen, 1u);
-    } else {
-      while (ld_acquire_u32(p.bar_gen) == gen) {
+// Grid barrier among the consumer threads of all CTAs.  Flag based: CTA c publishes epoch e with ONE release store to
+// its own 32-byte line; thread t of every CTA polls CTA t's line.  No atomic serialisation and a single L2 hop (the
+// atomic-counter + generation version cost ~5 us per barrier on 148 CTAs; 5 barriers per layer).  Epochs only grow and
+// persist across launches (every CTA passes the same number of barriers), so nothing needs resetting.
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch) {
+  ++epoch;
+  consumer_sync();  // every consumer thread's global writes of this phase happen-before thread 0's release below
+  if (tid == 0) st_release_u32(p.bar_flags + blockIdx.x * 8, epoch);
+  for (int c = tid; c < (int)gridDim.x; c += MK_CONSUMERS) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire_u32(p.bar_flags + c * 8) - epoch) < 0) {
+#ifdef MB200_MK_BARRIER_SLEEP
+      __nanosleep(32);
+#endif
+      if (++spins == MB200_WATCHDOG_SPINS) {
+        printf("[mb200 watchdog] block %d stuck in grid barrier epoch=%u waiting for block %d (flag=%u)\n", (int)blockIdx.x, epoch, c,
+               ld_acquire_u32(p.bar_flags + c * 8));
+        __trap();
       }
     }
-    __threadfence();
   }
   consumer_sync();
 }
@@ -163,16 +192,20 @@ struct RingState {
 
 // ---- producer: stream this CTA's slice of one matrix --------------------------------------------
 __device__ __forceinline__ void produce_matrix(const bf16* W, int N, int K, uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages,
-                                               RingState& rs) {
+                                               RingState& rs, int lane) {
   const MatCut c = cut_matrix(N, K);
   const uint32_t row_bytes = (uint32_t)c.kc * 2;
+  if (lane != 0) {  // one lane issues the (large) weight copies; the others only keep the stage counter in step
+    rs.it += (uint32_t)(c.p1 - c.p0) * c.nch;
+    return;
+  }
   for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
     const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
     for (int ch = 0; ch < c.nch; ++ch) {
       for (int w = 0; w < g; ++w) {
         const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
         const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
-        mbar_wait(&empty[slot], par ^ 1);
+        mbar_wait(&empty[slot], par ^ 1, 1, rs.it);
         uint8_t* dst = ring + (size_t)slot * MK_STAGE_BYTES;
         mbar_arrive_expect_tx(&full[slot], 2 * row_bytes);
         if (c.nch == 1) {
@@ -183,6 +216,49 @@ __device__ __forceinline__ void produce_matrix(const bf16* W, int N, int K, uint
         }
         ++rs.it;
       }
+    }
+  }
+}
+
+
+constexpr float kMaskedScore = -1.0e30f;
+
+// ---- attention slice of this CTA (same arithmetic in producer and consumers) ---------------------------------
+struct AttnSlice {
+  int C, k_begin, k_end, n_kvst, pps, n_slices;  // positions per CTA, my range, my K (= V) stage count, positions per stage
+};
+__device__ __forceinline__ AttnSlice attn_slice(const MkParams& p, int W) {
+  AttnSlice a;
+  const int len = min(p.pos + 1, W);
+  a.C = (len + (int)gridDim.x - 1) / (int)gridDim.x;
+  a.n_slices = (len + a.C - 1) / a.C;
+  a.k_begin = min((int)blockIdx.x * a.C, len);
+  a.k_end = min(a.k_begin + a.C, len);
+  a.pps = MK_STAGE_BYTES / (p.KV * kHeadDim * 2);
+  a.n_kvst = (a.k_end - a.k_begin + a.pps - 1) / a.pps;
+  return a;
+}
+
+// ---- producer: this CTA's K and V slice, alternating K / V stages of `pps` positions (contiguous bytes) ----------------
+__device__ __forceinline__ void produce_kv(const MkParams& p, const MkLayer& L, int W, uint8_t* ring, uint64_t* full, uint64_t* empty,
+                                           int n_stages, RingState& rs, int lane) {
+  const AttnSlice a = attn_slice(p, W);
+  if (lane != 0) {
+    rs.it += 2u * a.n_kvst;
+    return;
+  }
+  const int64_t row_elems = (int64_t)p.KV * kHeadDim;
+  const bf16* kbase = L.cache_k + ((int64_t)p.batch_row * W) * row_elems;
+  const bf16* vbase = L.cache_v + ((int64_t)p.batch_row * W) * row_elems;
+  for (int j = 0; j < a.n_kvst; ++j) {
+    const int k0 = a.k_begin + j * a.pps;
+    const uint32_t bytes = (uint32_t)min(a.pps, a.k_end - k0) * (uint32_t)row_elems * 2;
+#pragma unroll
+    for (int kv = 0; kv < 2; ++kv, ++rs.it) {
+      const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
+      mbar_wait(&empty[slot], par ^ 1, 4, rs.it);
+      mbar_arrive_expect_tx(&full[slot], bytes);
+      bulk_g2s(ring + (size_t)slot * MK_STAGE_BYTES, (kv ? vbase : kbase) + (int64_t)k0 * row_elems, bytes, &full[slot]);
     }
   }
 }
@@ -208,8 +284,8 @@ __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring
         // slot's PREVIOUS fill (owned by another warp) has landed; `full` would then still be one phase behind and a
         // parity wait would alias and pass early.  Waiting first until that previous fill has been CONSUMED (same
         // condition the producer waits for before refilling) pins `full` to phase {r, r+1} when it is tested.
-        mbar_wait(&empty[slot], par ^ 1);
-        mbar_wait(&full[slot], par);
+        mbar_wait(&empty[slot], par ^ 1, 2, it);
+        mbar_wait(&full[slot], par, 3, it);
         const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
         const uint4* w1 = w0 + kc8;
         const uint4* xc = xs + ch * kc8;
@@ -227,7 +303,7 @@ __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is the only reader of the slot
+        if (lane == 0) mbar_arrive_n(&empty[slot], MK_CONSUMER_WARPS);  // this warp is the only reader of the slot
       }
       a0 = warp_sum(a0);
       a1 = warp_sum(a1);
@@ -279,19 +355,19 @@ __device__ __forceinline__ void stage_x(uint4* xs, const bf16* src, const bf16* 
 
 __device__ __forceinline__ uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
 
-// ---- phase 2: flash-decoding over the ring for one (kv head, split) item, 8 warps ---------------------
+// ---- phase 2a: partial attention of this CTA's position slice, all heads, out of the ring ------------------------
+// All 8 warps wait for (and release) every K/V stage; warp w computes kv head w: half a warp per position (16 lanes x 16 B = the
+// head's 256-byte row), online softmax per (half-warp, query head) in registers, halves merged by shuffle at the end.
 template <int REP>
-__device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L, int W, int tid, float* sm_m, float* sm_l, float* sm_acc,
-                                             int* sm_flag) {
-  const int S = min(max((int)gridDim.x / p.KV, 1), MK_MAX_SPLITS);
-  const int item = blockIdx.x;
-  if (item >= p.KV * S) return;
-  const int g = item / S, s = item % S;
+__device__ __forceinline__ void mk_attention_slice(const MkParams& p, const MkLayer& L, int W, const uint8_t* ring, uint64_t* full,
+                                                   uint64_t* empty, int n_stages, RingState& rs, int tid) {
+  const AttnSlice a = attn_slice(p, W);
+  if (a.n_kvst == 0) return;
   const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
-  const int len = min(p.pos + 1, W);
-  const int C = (len + S - 1) / S;
-  const int k_begin = min(s * C, len), k_end = min(k_begin + C, len);
+  const bool has_head = warp < p.KV;
+  const int g = has_head ? warp : 0;
   const float scale = 0.08838834764831845f;
+  const int64_t row_elems = (int64_t)p.KV * kHeadDim;
 
   float qf[REP][8];
 #pragma unroll
@@ -304,76 +380,93 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
       qf[r][2 * j + 1] = bf16hi(u[j]);
     }
   }
+  // the row of the token being decoded was written in phase 1: the ring's copy of that slot may predate the write
+  const int cur = p.pos % W;
+  uint4 kcur = make_uint4(0, 0, 0, 0), vcur = kcur;
+  if (cur >= a.k_begin && cur < a.k_end) {
+    const int64_t off = ((int64_t)p.batch_row * W + cur) * row_elems + (int64_t)g * kHeadDim + hl * 8;
+    kcur = ldcg16(L.cache_k + off);
+    vcur = ldcg16(L.cache_v + off);
+  }
   float m[REP], l[REP], acc[REP][8];
 #pragma unroll
   for (int r = 0; r < REP; ++r) {
-    m[r] = -INFINITY;
+    m[r] = kMaskedScore;  // finite "minus infinity": (m - m) stays 0 instead of NaN, exp2 of the difference underflows to 0
     l[r] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
   }
-  const int64_t row_stride = (int64_t)p.KV * kHeadDim;
-  const bf16* kbase = L.cache_k + ((int64_t)p.batch_row * W) * row_stride + (int64_t)g * kHeadDim + hl * 8;
-  const bf16* vbase = L.cache_v + ((int64_t)p.batch_row * W) * row_stride + (int64_t)g * kHeadDim + hl * 8;
-  constexpr int STRIDE = MK_CONSUMER_WARPS * 2;
-  constexpr int PF = 5;  // keys in flight per half-warp beyond the current one (16 half-warps x 5 x 512 B = 40 KB per SM)
-  int slot = k_begin + warp * 2 + half;
-  uint4 kq[PF], vq[PF];
+
+  for (int j = 0; j < a.n_kvst; ++j) {
+    const uint32_t itk = rs.it + 2u * j, itv = itk + 1;
+    const uint32_t sk = itk % n_stages, pk = (itk / n_stages) & 1, sv = itv % n_stages, pv = (itv / n_stages) & 1;
+    mbar_wait(&full[sk], pk, 5, itk);  // every warp visits every K/V stage in order: never more than one lap from the barrier
+    mbar_wait(&full[sv], pv, 6, itv);
+    if (has_head) {
+      const int k0 = a.k_begin + j * a.pps;
+      const int nk = min(a.pps, a.k_end - k0);
+      const uint8_t* kst = ring + (size_t)sk * MK_STAGE_BYTES + g * (kHeadDim * 2) + hl * 16;
+      const uint8_t* vst = ring + (size_t)sv * MK_STAGE_BYTES + g * (kHeadDim * 2) + hl * 16;
+      // Branch-free on purpose: with `if (valid)` around the softmax update the compiler fences each head's chain
+      // (FFMA x8 -> 4 shuffles -> exp -> update, ~350 cycles) into its own reconvergence region and the four heads run
+      // back to back; as straight-line code (masked score = finite sentinel, p = 0) the chains interleave.
+#pragma unroll 2
+      for (int r2 = 0; r2 < (nk + 1) / 2; ++r2) {
+        const int row = 2 * r2 + half;
+        const bool valid = row < nk;
+        const int rr = valid ? row : 0;
+        const bool is_cur = (k0 + rr == cur);
+        uint4 kc = *reinterpret_cast<const uint4*>(kst + (size_t)rr * row_elems * 2);
+        uint4 vc = *reinterpret_cast<const uint4*>(vst + (size_t)rr * row_elems * 2);
+        kc.x = is_cur ? kcur.x : kc.x;
+        kc.y = is_cur ? kcur.y : kc.y;
+        kc.z = is_cur ? kcur.z : kc.z;
+        kc.w = is_cur ? kcur.w : kc.w;
+        vc.x = is_cur ? vcur.x : vc.x;
+        vc.y = is_cur ? vcur.y : vc.y;
+        vc.z = is_cur ? vcur.z : vc.z;
+        vc.w = is_cur ? vcur.w : vc.w;
+        const uint32_t ku[4] = {kc.x, kc.y, kc.z, kc.w}, vu[4] = {vc.x, vc.y, vc.z, vc.w};
+        float kf[8], vf[8];
 #pragma unroll
-  for (int u = 0; u < PF; ++u) {
-    kq[u] = vq[u] = make_uint4(0, 0, 0, 0);
-    const int sl = slot + u * STRIDE;
-    if (sl < k_end) {  // the slot of the current token was written by another CTA in phase 1: bypass L1
-      kq[u] = ldcg16(kbase + sl * row_stride);
-      vq[u] = ldcg16(vbase + sl * row_stride);
-    }
-  }
-  const int iters = (k_end - k_begin + STRIDE - 1) / STRIDE;
-  for (int it = 0; it < iters; ++it) {
-    const bool valid = slot < k_end;
-    const uint4 kc = kq[0], vc = vq[0];
+        for (int jj = 0; jj < 4; ++jj) {
+          kf[2 * jj] = bf16lo(ku[jj]);
+          kf[2 * jj + 1] = bf16hi(ku[jj]);
+          vf[2 * jj] = bf16lo(vu[jj]);
+          vf[2 * jj + 1] = bf16hi(vu[jj]);
+        }
 #pragma unroll
-    for (int u = 0; u + 1 < PF; ++u) {
-      kq[u] = kq[u + 1];
-      vq[u] = vq[u + 1];
-    }
-    const int nslot = slot + PF * STRIDE;
-    if (nslot < k_end) {
-      kq[PF - 1] = ldcg16(kbase + nslot * row_stride);
-      vq[PF - 1] = ldcg16(vbase + nslot * row_stride);
-    }
-    const uint32_t ku[4] = {kc.x, kc.y, kc.z, kc.w}, vu[4] = {vc.x, vc.y, vc.z, vc.w};
-    float kf[8], vf[8];
+        for (int r = 0; r < REP; ++r) {
+          float d = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      kf[2 * j] = bf16lo(ku[j]);
-      kf[2 * j + 1] = bf16hi(ku[j]);
-      vf[2 * j] = bf16lo(vu[j]);
-      vf[2 * j + 1] = bf16hi(vu[j]);
-    }
+          for (int jj = 0; jj < 8; ++jj) d = fmaf(qf[r][jj], kf[jj], d);
+          d += __shfl_xor_sync(0xffffffffu, d, 8);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          const float sc = valid ? d * scale : kMaskedScore;
+          const float mn = fmaxf(m[r], sc);
+          const float corr = exp2f((m[r] - mn) * kLog2e);
+          const float pe = exp2f((sc - mn) * kLog2e);
+          const float pr = valid ? pe : 0.f;
+          l[r] = l[r] * corr + pr;
 #pragma unroll
-    for (int r = 0; r < REP; ++r) {
-      float d = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d = fmaf(qf[r][j], kf[j], d);
-      d += __shfl_xor_sync(0xffffffffu, d, 8);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (valid) {
-        const float sc = d * scale;
-        const float mn = fmaxf(m[r], sc);
-        const float corr = exp2f((m[r] - mn) * kLog2e);
-        const float pr = exp2f((sc - mn) * kLog2e);
-        l[r] = l[r] * corr + pr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(pr, vf[j], acc[r][j] * corr);
-        m[r] = mn;
+          for (int jj = 0; jj < 8; ++jj) acc[r][jj] = fmaf(pr, vf[jj], acc[r][jj] * corr);
+          m[r] = mn;
+        }
       }
     }
-    slot += STRIDE;
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty[sk]);
+      mbar_arrive(&empty[sv]);
+    }
   }
-  // merge half-warps, then the 8 warps through shared memory
+  rs.it += 2u * a.n_kvst;
+  if (!has_head) return;
+  // merge the two half-warps and publish this slice's partial for the REP heads of kv head g
+  const int PSTRIDE = kHeadDim + 2;
+  float* mine = p.partial + ((int64_t)blockIdx.x * p.H + g * REP) * PSTRIDE;
 #pragma unroll
   for (int r = 0; r < REP; ++r) {
     const float mo = __shfl_xor_sync(0xffffffffu, m[r], 16);
@@ -381,75 +474,82 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
     const float mn = fmaxf(m[r], mo);
     const float cs = (m[r] == -INFINITY) ? 0.f : exp2f((m[r] - mn) * kLog2e);
     const float co = (mo == -INFINITY) ? 0.f : exp2f((mo - mn) * kLog2e);
-    l[r] = l[r] * cs + lo * co;
+    const float lt = l[r] * cs + lo * co;
+    float out[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float ao = __shfl_xor_sync(0xffffffffu, acc[r][j], 16);
-      acc[r][j] = acc[r][j] * cs + ao * co;
+    for (int jj = 0; jj < 8; ++jj) {
+      const float ao = __shfl_xor_sync(0xffffffffu, acc[r][jj], 16);
+      out[jj] = acc[r][jj] * cs + ao * co;
     }
-    m[r] = mn;
     if (half == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sm_acc[(warp * REP + r) * kHeadDim + hl * 8 + j] = acc[r][j];
-      if (hl == 0) {
-        sm_m[warp * REP + r] = m[r];
-        sm_l[warp * REP + r] = l[r];
-      }
+      float4* dst = reinterpret_cast<float4*>(mine + r * PSTRIDE + 2 + hl * 8);  // 8-byte aligned rows: use float2 stores
+      float2* d2 = reinterpret_cast<float2*>(dst);
+      d2[0] = make_float2(out[0], out[1]);
+      d2[1] = make_float2(out[2], out[3]);
+      d2[2] = make_float2(out[4], out[5]);
+      d2[3] = make_float2(out[6], out[7]);
+      if (hl == 0) *reinterpret_cast<float2*>(mine + r * PSTRIDE) = make_float2(mn, lt);
     }
   }
-  consumer_sync();
+}
+
+// ---- phase 2b: merge the slices.  Unit u = (query head, 32-dim quarter); warp w folds slices w, w+8, ... (all loads issued
+// before the first use), the 8 warps are folded through shared memory, lane = dim.
+constexpr int MK_CMB_MAX = 20;  // slices per warp held in registers at once
+__device__ __forceinline__ void mk_attention_combine(const MkParams& p, int W, int tid, float* scratch) {
+  const AttnSlice a = attn_slice(p, W);
+  const int lane = tid & 31, warp = tid >> 5;
   const int PSTRIDE = kHeadDim + 2;
-  float* mine = p.partial + (((int64_t)g * S + s) * REP) * PSTRIDE;
-  if (tid < kHeadDim) {
-    const int d = tid;
+  float* sm = scratch;  // [8 warps][34]: m, l, acc[32]
+  for (int u = blockIdx.x; u < p.H * 4; u += gridDim.x) {
+    const int h = u >> 2, q4 = u & 3;
+    float m = -INFINITY, l = 0.f, acc = 0.f;
+    for (int a0 = warp; a0 < a.n_slices; a0 += MK_CONSUMER_WARPS * MK_CMB_MAX) {
+      float mt[MK_CMB_MAX], lt[MK_CMB_MAX], at[MK_CMB_MAX];
 #pragma unroll
-    for (int r = 0; r < REP; ++r) {
+      for (int i = 0; i < MK_CMB_MAX; ++i) {
+        const int sl = a0 + i * MK_CONSUMER_WARPS;
+        mt[i] = -INFINITY;
+        lt[i] = at[i] = 0.f;
+        if (sl < a.n_slices) {
+          const float* pp = p.partial + ((int64_t)sl * p.H + h) * PSTRIDE;
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(pp));
+          mt[i] = ml.x;
+          lt[i] = ml.y;
+          at[i] = __ldcg(pp + 2 + q4 * 32 + lane);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MK_CMB_MAX; ++i) {
+        const float mn = fmaxf(m, mt[i]);
+        const float c0 = (m == -INFINITY) ? 0.f : exp2f((m - mn) * kLog2e);
+        const float c1 = (mt[i] == -INFINITY) ? 0.f : exp2f((mt[i] - mn) * kLog2e);
+        l = l * c0 + lt[i] * c1;
+        acc = acc * c0 + at[i] * c1;
+        m = mn;
+      }
+    }
+    sm[warp * 34 + 2 + lane] = acc;
+    if (lane == 0) {
+      sm[warp * 34] = m;
+      sm[warp * 34 + 1] = l;
+    }
+    consumer_sync();
+    if (warp == 0) {
       float mn = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < MK_CONSUMER_WARPS; ++w) mn = fmaxf(mn, sm_m[w * REP + r]);
+      for (int w = 0; w < MK_CONSUMER_WARPS; ++w) mn = fmaxf(mn, sm[w * 34]);
       float lt = 0.f, at = 0.f;
 #pragma unroll
       for (int w = 0; w < MK_CONSUMER_WARPS; ++w) {
-        const float mw = sm_m[w * REP + r];
+        const float mw = sm[w * 34];
         const float c = (mw == -INFINITY) ? 0.f : exp2f((mw - mn) * kLog2e);
-        lt += sm_l[w * REP + r] * c;
-        at += sm_acc[(w * REP + r) * kHeadDim + d] * c;
+        lt += sm[w * 34 + 1] * c;
+        at += sm[w * 34 + 2 + lane] * c;
       }
-      mine[r * PSTRIDE + 2 + d] = at;
-      if (d == 0) {
-        mine[r * PSTRIDE + 0] = mn;
-        mine[r * PSTRIDE + 1] = lt;
-      }
+      p.abuf[h * kHeadDim + q4 * 32 + lane] = __float2bfloat16_rn(at / lt);
     }
-    __threadfence();
-  }
-  consumer_sync();
-  if (tid == 0) {
-    const int prev = atomicAdd(&p.attn_counters[g], 1);
-    const int last = (prev == S - 1);
-    if (last) p.attn_counters[g] = 0;
-    *sm_flag = last;
-  }
-  consumer_sync();
-  if (!*sm_flag) return;
-  __threadfence();
-  if (tid < kHeadDim) {
-    const int d = tid;
-    const float* all = p.partial + ((int64_t)g * S) * REP * PSTRIDE;
-#pragma unroll
-    for (int r = 0; r < REP; ++r) {
-      float mn = -INFINITY;
-      for (int t = 0; t < S; ++t) mn = fmaxf(mn, __ldcg(all + ((int64_t)t * REP + r) * PSTRIDE));
-      float lt = 0.f, at = 0.f;
-      for (int t = 0; t < S; ++t) {
-        const float* pp = all + ((int64_t)t * REP + r) * PSTRIDE;
-        const float mt = __ldcg(pp);
-        const float c = (mt == -INFINITY) ? 0.f : exp2f((mt - mn) * kLog2e);
-        lt += __ldcg(pp + 1) * c;
-        at += __ldcg(pp + 2 + d) * c;
-      }
-      p.abuf[(g * REP + r) * kHeadDim + d] = __float2bfloat16_rn(at / lt);
-    }
+    consumer_sync();
   }
 }
 
@@ -462,17 +562,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + p.xs_bytes);
   uint64_t* empty = full + MK_MAX_STAGES;
   float* red = reinterpret_cast<float*>(empty + MK_MAX_STAGES);                       // [8]
-  int* sm_flag = reinterpret_cast<int*>(red + 8 + 32);
-  // attention merge scratch aliases the xs buffer (xs is dead during phase 2): m, l [8*REP], acc [8*REP*128]
-  float* sm_m = reinterpret_cast<float*>(xs);
-  float* sm_l = sm_m + MK_CONSUMER_WARPS * AD_MAX_REP;
-  float* sm_acc = sm_l + MK_CONSUMER_WARPS * AD_MAX_REP;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MK_CONSUMER_WARPS);  // weight stages: the owning warp arrives x8; K/V stages: every warp x1
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -483,21 +578,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   rs.it = 0;
 
   if (tid >= MK_CONSUMERS) {
-    // ================= producer warp (one lane issues; weights never wait for activations) =================
-    if (tid == MK_CONSUMERS) {
-      for (int l = 0; l < p.n_layers; ++l) {
-        const MkLayer L = p.layers[l];
-        produce_matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs);
-        produce_matrix(L.wo, p.dim, q_dim, ring, full, empty, p.n_stages, rs);
-        produce_matrix(L.w13, 2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs);
-        produce_matrix(L.w2, p.dim, p.hidden, ring, full, empty, p.n_stages, rs);
-      }
-      produce_matrix(p.w_out, p.vocab, p.dim, ring, full, empty, p.n_stages, rs);
+    // ================= producer warp (weights and old KV rows never wait for activations) =================
+    const int lane = tid - MK_CONSUMERS;
+    for (int l = 0; l < p.n_layers; ++l) {
+      const MkLayer L = p.layers[l];
+      produce_matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, lane);
+      produce_kv(p, L, p.windows[l], ring, full, empty, p.n_stages, rs, lane);
+      produce_matrix(L.wo, p.dim, q_dim, ring, full, empty, p.n_stages, rs, lane);
+      produce_matrix(L.w13, 2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, lane);
+      produce_matrix(L.w2, p.dim, p.hidden, ring, full, empty, p.n_stages, rs, lane);
     }
+    produce_matrix(p.w_out, p.vocab, p.dim, ring, full, empty, p.n_stages, rs, lane);
     return;
   }
 
   // ================= consumer warps =================
+  unsigned epoch = ld_acquire_u32(p.bar_flags + blockIdx.x * 8);  // this CTA's own flag: the epoch the last launch ended on
   const int64_t token = *p.token;
   for (int l = 0; l < p.n_layers; ++l) {
     const MkLayer L = p.layers[l];
@@ -531,13 +627,17 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       });
     }
     mk_stamp(p, tid, l, 2);
-    grid_barrier(p, tid);
+    grid_barrier(p, tid, epoch);
     mk_stamp(p, tid, l, 3);
 
-    // ---- phase 2: attention over the ring ----
-    mk_attention<REP>(p, L, W, tid, sm_m, sm_l, sm_acc, sm_flag);
+    // ---- phase 2a: partial attention of my position slice;  2b: merge the slices ----
+    mk_attention_slice<REP>(p, L, W, ring, full, empty, p.n_stages, rs, tid);
+    mk_stamp(p, tid, l, 12);
+    grid_barrier(p, tid, epoch);
+    mk_stamp(p, tid, l, 13);
+    mk_attention_combine(p, W, tid, reinterpret_cast<float*>(xs));
     mk_stamp(p, tid, l, 4);
-    grid_barrier(p, tid);
+    grid_barrier(p, tid, epoch);
     mk_stamp(p, tid, l, 5);
 
     // ---- phase 3: wo + residual ----
@@ -547,7 +647,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
     mk_stamp(p, tid, l, 6);
-    grid_barrier(p, tid);
+    grid_barrier(p, tid, epoch);
     mk_stamp(p, tid, l, 7);
 
     // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
@@ -557,7 +657,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
     });
     mk_stamp(p, tid, l, 8);
-    grid_barrier(p, tid);
+    grid_barrier(p, tid, epoch);
     mk_stamp(p, tid, l, 9);
 
     // ---- phase 5: down + residual ----
@@ -567,7 +667,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
     mk_stamp(p, tid, l, 10);
-    grid_barrier(p, tid);
+    grid_barrier(p, tid, epoch);
     mk_stamp(p, tid, l, 11);
   }
 

@@ -21,7 +21,7 @@ cache._kv_seqlens_host = [5000]
 tok = torch.tensor([17], device="cuda")
 for _ in range(3):
     model.decode_static(tok, cache)
-buf = torch.zeros(L * 12, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * L * 16, dtype=torch.int64, device="cuda")
 _abi.set_decode_timeline(buf)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -29,12 +29,23 @@ model.decode_static(tok, cache)
 e1.record()
 torch.cuda.synchronize()
 _abi.set_decode_timeline(None)
-t = buf.cpu().view(L, 12).double()
+t = buf.cpu().view(8, L, 16).double() / 1000.0  # us; 8 sampled CTAs (0, 21, ..., 147)
 names = ["stage_x+norm", "QKV gemv", "barrier1", "attention", "barrier2", "stage+WO gemv", "barrier3", "stage+GATEUP", "barrier4",
          "stage+DOWN", "barrier5"]
-d = (t[:, 1:] - t[:, :-1]) / 1000.0  # us
-print(f"kernel total {e0.elapsed_time(e1) * 1000:.1f} us for {L} layers; per-layer phase durations of CTA 0 (us), median over layers 1..:")
-med = d[1:].median(0).values
-for n, v in zip(names, med.tolist()):
-    print(f"  {n:16s} {v:8.2f}")
-print(f"  {'layer total':16s} {((t[1:, 11] - t[1:, 0]) / 1000).median().item():8.2f}   (ideal HBM time per layer at 6583 GB/s: {(436.2e6 + 16.8e6) / 6583.5e3:.1f} us)")
+d = t[:, :, 1:12] - t[:, :, :11]
+print(f"kernel total {e0.elapsed_time(e1) * 1000:.1f} us for {L} layers; phase durations (us), median over layers 1.., per sampled CTA min / CTA 0 / max:")
+med = d[:, 1:].median(1).values  # [8, 11]
+for i, n in enumerate(names):
+    print(f"  {n:16s} min {med[:, i].min():7.2f}   cta0 {med[0, i]:7.2f}   max {med[:, i].max():7.2f}")
+arr = t[:, 1:, [2, 4, 6, 8, 10]]  # arrival times at the 5 barriers
+lea = t[:, 1:, [3, 5, 7, 9, 11]]  # leave times
+skew = (arr.max(0).values - arr.min(0).values).median(0).values
+lat = (lea.min(0).values - arr.max(0).values).median(0).values
+a = t[:6, 1:]  # active sampled CTAs
+sub = torch.stack([a[:, :, 12] - a[:, :, 3], a[:, :, 13] - a[:, :, 12], a[:, :, 4] - a[:, :, 13]], -1).median(1).values
+print("  inside attention (us; slice partial | mid barrier | slice merge), per sampled CTA:")
+for row in sub.tolist():
+    print("     ", [round(x, 2) for x in row])
+print("  barrier arrival skew across sampled CTAs (us):", [round(x, 2) for x in skew.tolist()])
+print("  barrier latency last-arrival -> first-leave (us):", [round(x, 2) for x in lat.tolist()])
+print(f"  layer total (cta0) {(t[0, 1:, 11] - t[0, 1:, 0]).median().item():8.2f}   (ideal HBM time per layer at 6583 GB/s: {(436.2e6 + 16.8e6) / 6583.5e3:.1f} us)")

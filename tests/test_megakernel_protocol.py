@@ -30,12 +30,17 @@ class Mbar:
 
 
 def stage_sequence(pairs_per_matrix, nch_per_matrix, grouped):
-    """Yields per matrix the list of (it, pair, ch, owner_warp) in PRODUCTION order."""
+    """Yields per matrix the list of (it, pair, ch, owner_warp) in PRODUCTION order.  nch == 0 marks the K/V slice stages of
+    the attention phase: `pairs` stages, each consumed by ALL warps (owner -1)."""
     it = 0
     mats = []
     for pairs, nch in zip(pairs_per_matrix, nch_per_matrix):
         seq = []
-        if grouped:
+        if nch == 0:
+            for j in range(pairs):
+                seq.append((it, j, 0, -1))
+                it += 1
+        elif grouped:
             for g0 in range(0, pairs, WARPS):
                 g = min(WARPS, pairs - g0)
                 for ch in range(nch):
@@ -57,7 +62,7 @@ def simulate(pairs_per_matrix, nch_per_matrix, n_stages, grouped, seed, max_step
     rng = random.Random(seed)
     mats = stage_sequence(pairs_per_matrix, nch_per_matrix, grouped)
     full = [Mbar(1) for _ in range(n_stages)]
-    empty = [Mbar(1) for _ in range(n_stages)]
+    empty = [Mbar(WARPS) for _ in range(n_stages)]  # weight stages: the owner arrives x8; K/V stages: every warp x1
     slot_data = [None] * n_stages
     inflight = []  # (slot, it): bulk copies issued, not yet landed
     prod = [s for m in mats for s in m]
@@ -66,7 +71,11 @@ def simulate(pairs_per_matrix, nch_per_matrix, n_stages, grouped, seed, max_step
     progs = [[] for _ in range(WARPS)]
     bar_id = 0
     for m in mats:
-        if grouped:
+        if m and m[0][3] == -1:  # K/V stages: every warp waits on every stage in order (no guard needed), arrives once
+            for w in range(WARPS):
+                for (it, p, ch, ww) in m:
+                    progs[w].append(("kvstage", it))
+        elif grouped:
             groups = {}
             for (it, p, ch, w) in m:
                 groups.setdefault(p // WARPS, []).append((it, p, ch, w))
@@ -102,7 +111,7 @@ def simulate(pairs_per_matrix, nch_per_matrix, n_stages, grouped, seed, max_step
                 if kind == "prev":
                     if empty[arg % n_stages].test(((arg // n_stages) & 1) ^ 1):
                         actors.append(("prevpass", w))
-                elif kind == "stage":
+                elif kind in ("stage", "kvstage"):
                     if full[arg % n_stages].test((arg // n_stages) & 1):
                         actors.append(("cons", w))
                 else:
@@ -127,7 +136,8 @@ def simulate(pairs_per_matrix, nch_per_matrix, n_stages, grouped, seed, max_step
             it = progs[w][pc[w]][1]
             if slot_data[it % n_stages] != it:
                 return "stale"
-            empty[it % n_stages].arrive()
+            for _k in range(1 if progs[w][pc[w]][0] == "kvstage" else WARPS):
+                empty[it % n_stages].arrive()
             pc[w] += 1
         elif a[0] == "prevpass":
             pc[a[1]] += 1
@@ -143,6 +153,9 @@ SHAPES = [
     ([24, 17, 97, 17, 443], [2, 1, 2, 4, 2], 12),   # Nemo-like: dim 5120 -> 2 chunks
     ([3, 1, 7, 1, 2], [1, 1, 1, 1, 1], 12),         # tiny test model
     ([21, 14, 97, 14, 108], [1, 1, 1, 4, 1], 9),    # smallest legal ring
+    ([21, 8, 14, 97, 14, 108], [1, 0, 1, 1, 4, 1], 12),  # with 8 K/V slice stages (all warps consume) between QKV and wo
+    ([21, 60, 14, 97, 14, 108], [1, 0, 1, 1, 4, 1], 12),  # long context: the K/V slice is several laps of the ring
+    ([24, 8, 17, 97, 17, 443], [2, 0, 1, 2, 4, 2], 9),
 ]
 
 
