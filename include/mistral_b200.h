@@ -171,6 +171,8 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
 /* Debug: a device buffer of n_layers*12 uint64 that mb200_decode_step fills with %globaltimer stamps at every phase
  * boundary of CTA 0 (NULL switches it off).  Used by scripts/mk_timeline.py to see where a decode step spends time. */
 int mb200_debug_set_decode_timeline(void* device_buffer);
+/* Debug: [n_sm][n_layers][6][2] uint64 arrive/leave stamps of every CTA at every grid barrier (NULL = off). */
+int mb200_debug_set_barrier_timeline(void* device_buffer);
 
 /* Test-only: CUDA-core fp32 GEMM c[T, N] = a[T, K] w[N, K]^T used to cross-check the tensor-core kernels. */
 int mb200_test_gemm_naive(const void* a, const void* w, float* c, int64_t T, int64_t N, int64_t K, void* stream);

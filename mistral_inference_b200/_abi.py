@@ -41,6 +41,7 @@ _SIGNATURES = {
     "mb200_decode_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "mb200_debug_set_decode_timeline": (c_int, [c_void_p]),
+    "mb200_debug_set_barrier_timeline": (c_int, [c_void_p]),
     "mb200_test_gemm_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
 }
 
@@ -180,6 +181,10 @@ def decode_step(layers_dev, windows_dev, n_layers, emb, final_norm, w_out, rope,
 
 def set_decode_timeline(buf: Optional[torch.Tensor]) -> None:
     _check(lib().mb200_debug_set_decode_timeline(_ptr(buf)), "mb200_debug_set_decode_timeline")
+
+
+def set_barrier_timeline(buf: Optional[torch.Tensor]) -> None:
+    _check(lib().mb200_debug_set_barrier_timeline(_ptr(buf)), "mb200_debug_set_barrier_timeline")
 
 
 def test_gemm_naive(a, w) -> torch.Tensor:

@@ -8,7 +8,8 @@
 
 namespace mb200 {
 thread_local char g_err[512] = "";
-static unsigned long long* g_mk_prof = nullptr;  // debug: decode megakernel phase timeline buffer (device)
+static unsigned long long* g_mk_prof = nullptr;
+static unsigned long long* g_mk_prof_bar = nullptr;  // debug: decode megakernel phase timeline buffer (device)
 
 constexpr size_t kWsHeader = 64 * 1024;  // persistent, zero-initialised by the caller once: self-resetting counters
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -239,6 +240,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   const int rep = (int)(n_heads / n_kv_heads);
   const int64_t q_dim = n_heads * head_dim;
   auto cut_ok = [](int64_t K) { const int64_t nch = (K + MK_MAX_KC - 1) / MK_MAX_KC; return K % (nch * 8) == 0; };
+  MB_CHECK_ARG(n_kv_heads * kHeadDim * 2 + MK_KV_PAD <= MK_STAGE_BYTES / 8, "decode_step: a ring stage must hold 8 padded K/V position rows");
   MB_CHECK_ARG(cut_ok(dim) && cut_ok(hidden) && cut_ok(q_dim), "decode_step: dim/hidden/q_dim must split into 16-byte-aligned row chunks");
   MB_CHECK_ARG(vocab % 2 == 0 && hidden % 1 == 0, "decode_step: vocab must be even");
   int dev = 0, sms = 0, smem_max = 0, coop = 0;
@@ -297,6 +299,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.gbuf = (bf16*)take((size_t)hidden * 2);
   p.partial = (float*)take((size_t)sms * n_heads * (kHeadDim + 2) * sizeof(float));  // [slice = CTA][H][m, l, acc[128]]
   p.prof = g_mk_prof;
+  p.prof_bar = g_mk_prof_bar;
   if (workspace_bytes < off) return fail(MB200_E_WORKSPACE, "decode_step: workspace %zu < %zu", workspace_bytes, off);
 
   void* args[] = {(void*)&p};
@@ -317,6 +320,10 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
 // Debug: device buffer of n_layers*12 uint64 that CTA 0 of the decode megakernel fills with %globaltimer stamps (NULL = off).
 int mb200_debug_set_decode_timeline(void* device_buffer) {
   g_mk_prof = (unsigned long long*)device_buffer;
+  return MB200_OK;
+}
+int mb200_debug_set_barrier_timeline(void* device_buffer) {
+  g_mk_prof_bar = (unsigned long long*)device_buffer;
   return MB200_OK;
 }
 

@@ -26,14 +26,17 @@
 #pragma once
 #include "attn_decode.cuh"
 #include "common.cuh"
+#include "gemm_mma.cuh"
 
 namespace mb200 {
 
 constexpr int MK_CONSUMER_WARPS = 8;
 constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
 constexpr int MK_THREADS = MK_CONSUMERS + 32;  // + producer warp
-constexpr int MK_STAGE_BYTES = 16 * 1024;
-constexpr int MK_MAX_KC = MK_STAGE_BYTES / 4;  // elements per row chunk (2 rows x KC x 2 B per stage)
+constexpr int MK_WEIGHT_STAGE_BYTES = 16 * 1024;   // a weight stage: 2 rows x KC elements x 2 B
+constexpr int MK_MAX_KC = MK_WEIGHT_STAGE_BYTES / 4;  // elements per row chunk
+constexpr int MK_KV_PAD = 16;                      // K/V position rows are laid out with a 16-byte pad (ldmatrix bank spread)
+constexpr int MK_STAGE_BYTES = 16 * 1024 + 16 * MK_KV_PAD;  // ring slot stride: also fits 8 padded 2 KB K/V position rows
 constexpr int MK_MAX_STAGES = 12;
 constexpr int MK_MAX_SPLITS = 32;
 
@@ -72,6 +75,7 @@ struct MkParams {
   bf16* abuf;           // [H*hd] attention output
   bf16* gbuf;           // [hidden]
   float* partial;       // [KV][splits][REP][hd+2]
+  unsigned long long* prof_bar;  // optional [gridDim][n_layers][6][2] arrive/leave %globaltimer of every CTA at every barrier
   unsigned long long* prof;  // optional [n_layers][12] globaltimer stamps written by CTA 0 (debug timeline), or null
 };
 
@@ -147,8 +151,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch) {
+__device__ __forceinline__ void bar_stamp(const MkParams& p, int tid, int layer, int which, int leave) {
+  if (p.prof_bar != nullptr && tid == 0 && layer >= 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.prof_bar[(((int64_t)blockIdx.x * p.n_layers + layer) * 6 + which) * 2 + leave] = t;
+  }
+}
+__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch, int layer = -1, int which = 0) {
   ++epoch;
+  bar_stamp(p, tid, layer, which, 0);
   consumer_sync();  // every consumer thread's global writes of this phase happen-before thread 0's release below
   if (tid == 0) st_release_u32(p.bar_flags + blockIdx.x * 8, epoch);
   for (int c = tid; c < (int)gridDim.x; c += MK_CONSUMERS) {
@@ -165,6 +177,7 @@ __device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigne
     }
   }
   consumer_sync();
+  bar_stamp(p, tid, layer, which, 1);
 }
 
 // How a [N, K] matrix is cut for the ring: pairs of rows, K in `nch` chunks of `kc` elements.
@@ -190,37 +203,6 @@ struct RingState {
 // So warp w touches stages base + ch*g + w: never more than 8 apart, i.e. always within one lap of the (>= 9-stage) ring --
 // which is what makes parity-based mbarrier waits safe (a waiter two laps ahead would alias and pass early).
 
-// ---- producer: stream this CTA's slice of one matrix --------------------------------------------
-__device__ __forceinline__ void produce_matrix(const bf16* W, int N, int K, uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages,
-                                               RingState& rs, int lane) {
-  const MatCut c = cut_matrix(N, K);
-  const uint32_t row_bytes = (uint32_t)c.kc * 2;
-  if (lane != 0) {  // one lane issues the (large) weight copies; the others only keep the stage counter in step
-    rs.it += (uint32_t)(c.p1 - c.p0) * c.nch;
-    return;
-  }
-  for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
-    const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
-    for (int ch = 0; ch < c.nch; ++ch) {
-      for (int w = 0; w < g; ++w) {
-        const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
-        const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
-        mbar_wait(&empty[slot], par ^ 1, 1, rs.it);
-        uint8_t* dst = ring + (size_t)slot * MK_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[slot], 2 * row_bytes);
-        if (c.nch == 1) {
-          bulk_g2s(dst, r0, 2 * row_bytes, &full[slot]);  // the two rows are contiguous
-        } else {
-          bulk_g2s(dst, r0 + ch * c.kc, row_bytes, &full[slot]);
-          bulk_g2s(dst + row_bytes, r0 + K + ch * c.kc, row_bytes, &full[slot]);
-        }
-        ++rs.it;
-      }
-    }
-  }
-}
-
-
 constexpr float kMaskedScore = -1.0e30f;
 
 // ---- attention slice of this CTA (same arithmetic in producer and consumers) ---------------------------------
@@ -234,33 +216,104 @@ __device__ __forceinline__ AttnSlice attn_slice(const MkParams& p, int W) {
   a.n_slices = (len + a.C - 1) / a.C;
   a.k_begin = min((int)blockIdx.x * a.C, len);
   a.k_end = min(a.k_begin + a.C, len);
-  a.pps = MK_STAGE_BYTES / (p.KV * kHeadDim * 2);
+  a.pps = min(16, (MK_STAGE_BYTES / (p.KV * kHeadDim * 2 + MK_KV_PAD)) & ~7);  // 8 or 16 positions per stage (one MMA key block)
   a.n_kvst = (a.k_end - a.k_begin + a.pps - 1) / a.pps;
   return a;
 }
 
-// ---- producer: this CTA's K and V slice, alternating K / V stages of `pps` positions (contiguous bytes) ----------------
-__device__ __forceinline__ void produce_kv(const MkParams& p, const MkLayer& L, int W, uint8_t* ring, uint64_t* full, uint64_t* empty,
-                                           int n_stages, RingState& rs, int lane) {
-  const AttnSlice a = attn_slice(p, W);
-  if (lane != 0) {
-    rs.it += 2u * a.n_kvst;
-    return;
+// ---- producer (one thread) ---------------------------------------------------------------------------------------------
+// The CTA's whole schedule (every layer: QKV slice, K/V slice, wo, gate/up, down slices; then the lm-head slice) is a pure
+// function of (blockIdx, shapes, pos), so the producer simply walks it, blocking only on free ring slots.  Its per-stage
+// budget is ~350 cycles (5.5 stages/us per SM at the HBM share of one SM): keep these loops lean -- a generic "schedule
+// iterator" version (needed for a second, L2-prefetch cursor) cost 5 % end to end on its own.
+// Experiment on record: running cp.async.bulk.prefetch.L2 D stages ahead to use the L2 as a second-level ring
+// made things WORSE on B200 (3.4 -> 4.3 ms/token at D = 16, 5.0 at D = 64): the prefetched lines do not survive until the copy.
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+struct Producer {
+  uint8_t* ring;
+  uint64_t* full;
+  uint64_t* empty;
+  int n_stages;
+  uint32_t it;
+  uint64_t policy;  // L2 evict-first: weights and old K/V rows are read exactly once per token
+
+  __device__ __forceinline__ uint8_t* acquire(uint32_t bytes, uint64_t*& bar) {
+    const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
+    mbar_wait(&empty[slot], par ^ 1, 1, it);
+    bar = &full[slot];
+    mbar_arrive_expect_tx(bar, bytes);
+    ++it;
+    return ring + (size_t)slot * MK_STAGE_BYTES;
   }
-  const int64_t row_elems = (int64_t)p.KV * kHeadDim;
-  const bf16* kbase = L.cache_k + ((int64_t)p.batch_row * W) * row_elems;
-  const bf16* vbase = L.cache_v + ((int64_t)p.batch_row * W) * row_elems;
-  for (int j = 0; j < a.n_kvst; ++j) {
-    const int k0 = a.k_begin + j * a.pps;
-    const uint32_t bytes = (uint32_t)min(a.pps, a.k_end - k0) * (uint32_t)row_elems * 2;
-#pragma unroll
-    for (int kv = 0; kv < 2; ++kv, ++rs.it) {
-      const uint32_t slot = rs.it % n_stages, par = (rs.it / n_stages) & 1;
-      mbar_wait(&empty[slot], par ^ 1, 4, rs.it);
-      mbar_arrive_expect_tx(&full[slot], bytes);
-      bulk_g2s(ring + (size_t)slot * MK_STAGE_BYTES, (kv ? vbase : kbase) + (int64_t)k0 * row_elems, bytes, &full[slot]);
+
+  // this CTA's slice of one [N, K] weight matrix, in the stage order consume_matrix expects
+  __device__ __forceinline__ void matrix(const bf16* W, int N, int K) {
+    const MatCut c = cut_matrix(N, K);
+    const uint32_t row_bytes = (uint32_t)c.kc * 2;
+    for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
+      const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
+      for (int ch = 0; ch < c.nch; ++ch) {
+        for (int w = 0; w < g; ++w) {
+          const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
+          uint64_t* bar;
+          uint8_t* dst = acquire(2 * row_bytes, bar);
+          if (c.nch == 1) {
+            bulk_g2s_hint(dst, r0, 2 * row_bytes, bar, policy);  // the two rows are contiguous
+          } else {
+            bulk_g2s_hint(dst, r0 + ch * c.kc, row_bytes, bar, policy);
+            bulk_g2s_hint(dst + row_bytes, r0 + K + ch * c.kc, row_bytes, bar, policy);
+          }
+        }
+      }
     }
   }
+
+  // this CTA's K and V slice: alternating K / V stages of `pps` positions; one copy per position row so that rows sit
+  // (row_bytes + 16) apart in shared memory (8 consecutive rows then cover all 32 banks for ldmatrix)
+  __device__ __forceinline__ void kv_slice(const MkParams& p, const MkLayer& L, int W) {
+    const AttnSlice a = attn_slice(p, W);
+    const int64_t row_elems = (int64_t)p.KV * kHeadDim;
+    const uint32_t row_bytes = (uint32_t)row_elems * 2;
+    const bf16* kbase = L.cache_k + ((int64_t)p.batch_row * W) * row_elems;
+    const bf16* vbase = L.cache_v + ((int64_t)p.batch_row * W) * row_elems;
+    for (int j = 0; j < a.n_kvst; ++j) {
+      const int k0 = a.k_begin + j * a.pps;
+      const int rows = min(a.pps, a.k_end - k0);
+#pragma unroll
+      for (int kv = 0; kv < 2; ++kv) {
+        uint64_t* bar;
+        uint8_t* dst = acquire((uint32_t)rows * row_bytes, bar);
+        const bf16* src = (kv ? vbase : kbase) + (int64_t)k0 * row_elems;
+        for (int r = 0; r < rows; ++r) bulk_g2s_hint(dst + r * (row_bytes + MK_KV_PAD), src + (int64_t)r * row_elems, row_bytes, bar, policy);
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+  Producer pr;
+  pr.ring = ring;
+  pr.full = full;
+  pr.empty = empty;
+  pr.n_stages = p.n_stages;
+  pr.it = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.policy));
+  const int q_dim = p.H * kHeadDim, kv_dim = p.KV * kHeadDim;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const MkLayer L = p.layers[l];
+    pr.matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim);
+    pr.kv_slice(p, L, p.windows[l]);
+    pr.matrix(L.wo, p.dim, q_dim);
+    pr.matrix(L.w13, 2 * p.hidden, p.dim);
+    pr.matrix(L.w2, p.dim, p.hidden);
+  }
+  pr.matrix(p.w_out, p.vocab, p.dim);
 }
 
 // ---- consumers: y[pair] = W[pair rows] . xs, epilogue(pair, acc0, acc1) on one lane ----------------
@@ -355,104 +408,135 @@ __device__ __forceinline__ void stage_x(uint4* xs, const bf16* src, const bf16* 
 
 __device__ __forceinline__ uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
 
-// ---- phase 2a: partial attention of this CTA's position slice, all heads, out of the ring ------------------------
-// All 8 warps wait for (and release) every K/V stage; warp w computes kv head w: half a warp per position (16 lanes x 16 B = the
-// head's 256-byte row), online softmax per (half-warp, query head) in registers, halves merged by shuffle at the end.
-template <int REP>
-__device__ __forceinline__ void mk_attention_slice(const MkParams& p, const MkLayer& L, int W, const uint8_t* ring, uint64_t* full,
-                                                   uint64_t* empty, int n_stages, RingState& rs, int tid) {
+// ---- phase 2a: partial attention of this CTA's position slice, all heads, out of the ring, on tensor cores --------------
+// Warp w serves kv head w.  Per K/V stage pair (PPS = 8 or 16 positions = one key block) it computes
+//   S[16 x PPS] = Q[16 x 128] K^T   with the REP query heads of the group as MMA rows 0..REP-1 (the other rows are zero),
+//   online softmax on the accumulator fragments (fp32), P rounded to bf16 as the A operand, O[16 x 128] += P V.
+// A CUDA-core version of the same loop (half a warp per key, shuffle-reduced dot products) is ISSUE bound: ~48 instructions
+// per (key, head), 5.6 us per layer at kv_len 4096; this form is ~25x fewer instructions.  mma.sync (not tcgen05): the tiles
+// are tiny and the softmax lives in registers; the tensor pipe is idle otherwise.
+// All 8 warps wait for (and release) every K/V stage; a warp touches only its own head's 256-byte segment of each row, so the
+// fresh row of the token being decoded and the zero-fill of rows past the slice are patched per warp, without block syncs.
+template <int REP, int PPS>
+__device__ __forceinline__ void mk_attention_slice(const MkParams& p, const MkLayer& L, int W, uint8_t* ring, uint64_t* full, uint64_t* empty,
+                                                   int n_stages, RingState& rs, int tid, int layer) {
+  static_assert(REP <= 8, "query heads of a group are MMA rows 0..7");
   const AttnSlice a = attn_slice(p, W);
   if (a.n_kvst == 0) return;
-  const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
+  const int lane = tid & 31, warp = tid >> 5;
   const bool has_head = warp < p.KV;
   const int g = has_head ? warp : 0;
-  const float scale = 0.08838834764831845f;
+  const int row = lane >> 2, cq = lane & 3;  // accumulator fragment: row = lane/4, column pair = lane%4
+  const float sl2 = 0.08838834764831845f * kLog2e;  // scores are scaled by hd^-0.5; softmax in the exp2 domain
   const int64_t row_elems = (int64_t)p.KV * kHeadDim;
+  const uint32_t row_stride = (uint32_t)row_elems * 2 + MK_KV_PAD;  // bytes between position rows in a stage
 
-  float qf[REP][8];
+  // Q as A fragments: a0 = (row, k..k+1), a2 = (row, k+8..k+9); rows >= REP and the row+8 halves are zero
+  uint32_t qa[8][4];
 #pragma unroll
-  for (int r = 0; r < REP; ++r) {
-    const uint4 v = ldcg16(p.qbuf + (g * REP + r) * kHeadDim + hl * 8);
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      qf[r][2 * j] = bf16lo(u[j]);
-      qf[r][2 * j + 1] = bf16hi(u[j]);
+  for (int ks = 0; ks < 8; ++ks) {
+    qa[ks][0] = qa[ks][1] = qa[ks][2] = qa[ks][3] = 0u;
+    if (row < REP) {
+      const bf16* qp = p.qbuf + (g * REP + row) * kHeadDim + ks * 16 + cq * 2;
+      qa[ks][0] = ldcg_u32(qp);
+      qa[ks][2] = ldcg_u32(qp + 8);
     }
   }
-  // the row of the token being decoded was written in phase 1: the ring's copy of that slot may predate the write
+  // the row of the token being decoded was written in phase 1: lanes 0-15 hold its K segment, lanes 16-31 its V segment
   const int cur = p.pos % W;
-  uint4 kcur = make_uint4(0, 0, 0, 0), vcur = kcur;
+  uint4 cur_kv = make_uint4(0, 0, 0, 0);
   if (cur >= a.k_begin && cur < a.k_end) {
-    const int64_t off = ((int64_t)p.batch_row * W + cur) * row_elems + (int64_t)g * kHeadDim + hl * 8;
-    kcur = ldcg16(L.cache_k + off);
-    vcur = ldcg16(L.cache_v + off);
+    const bf16* base = (lane < 16 ? L.cache_k : L.cache_v);
+    cur_kv = ldcg16(base + ((int64_t)p.batch_row * W + cur) * row_elems + (int64_t)g * kHeadDim + (lane & 15) * 8);
   }
-  float m[REP], l[REP], acc[REP][8];
+  float o[16][4];
 #pragma unroll
-  for (int r = 0; r < REP; ++r) {
-    m[r] = kMaskedScore;  // finite "minus infinity": (m - m) stays 0 instead of NaN, exp2 of the difference underflows to 0
-    l[r] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-  }
+  for (int n = 0; n < 16; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m_run = kMaskedScore, l_run = 0.f;  // state of row `row` (this lane's share of l; reduced over the 4 lanes at the end)
 
   for (int j = 0; j < a.n_kvst; ++j) {
     const uint32_t itk = rs.it + 2u * j, itv = itk + 1;
     const uint32_t sk = itk % n_stages, pk = (itk / n_stages) & 1, sv = itv % n_stages, pv = (itv / n_stages) & 1;
     mbar_wait(&full[sk], pk, 5, itk);  // every warp visits every K/V stage in order: never more than one lap from the barrier
     mbar_wait(&full[sv], pv, 6, itv);
+    if (j == 0) mk_stamp(p, tid, layer, 14);
+    if (j == a.n_kvst - 1) mk_stamp(p, tid, layer, 15);
     if (has_head) {
-      const int k0 = a.k_begin + j * a.pps;
-      const int nk = min(a.pps, a.k_end - k0);
-      const uint8_t* kst = ring + (size_t)sk * MK_STAGE_BYTES + g * (kHeadDim * 2) + hl * 16;
-      const uint8_t* vst = ring + (size_t)sv * MK_STAGE_BYTES + g * (kHeadDim * 2) + hl * 16;
-      // Branch-free on purpose: with `if (valid)` around the softmax update the compiler fences each head's chain
-      // (FFMA x8 -> 4 shuffles -> exp -> update, ~350 cycles) into its own reconvergence region and the four heads run
-      // back to back; as straight-line code (masked score = finite sentinel, p = 0) the chains interleave.
-#pragma unroll 2
-      for (int r2 = 0; r2 < (nk + 1) / 2; ++r2) {
-        const int row = 2 * r2 + half;
-        const bool valid = row < nk;
-        const int rr = valid ? row : 0;
-        const bool is_cur = (k0 + rr == cur);
-        uint4 kc = *reinterpret_cast<const uint4*>(kst + (size_t)rr * row_elems * 2);
-        uint4 vc = *reinterpret_cast<const uint4*>(vst + (size_t)rr * row_elems * 2);
-        kc.x = is_cur ? kcur.x : kc.x;
-        kc.y = is_cur ? kcur.y : kc.y;
-        kc.z = is_cur ? kcur.z : kc.z;
-        kc.w = is_cur ? kcur.w : kc.w;
-        vc.x = is_cur ? vcur.x : vc.x;
-        vc.y = is_cur ? vcur.y : vc.y;
-        vc.z = is_cur ? vcur.z : vc.z;
-        vc.w = is_cur ? vcur.w : vc.w;
-        const uint32_t ku[4] = {kc.x, kc.y, kc.z, kc.w}, vu[4] = {vc.x, vc.y, vc.z, vc.w};
-        float kf[8], vf[8];
+      const int k0 = a.k_begin + j * PPS;
+      const int nk = min(PPS, a.k_end - k0);
+      uint8_t* kst = ring + (size_t)sk * MK_STAGE_BYTES + g * (kHeadDim * 2);
+      uint8_t* vst = ring + (size_t)sv * MK_STAGE_BYTES + g * (kHeadDim * 2);
+      // patches (own 256-byte segments only): fresh current-token row; zero the V rows past the slice (P = 0 there, but 0 * NaN)
+      if (cur >= k0 && cur < k0 + nk)
+        *reinterpret_cast<uint4*>((lane < 16 ? kst : vst) + (size_t)(cur - k0) * row_stride + (lane & 15) * 16) = cur_kv;
+      if (nk < PPS)
+        for (int r = nk + (lane >> 4); r < PPS; r += 2) *reinterpret_cast<uint4*>(vst + (size_t)r * row_stride + (lane & 15) * 16) = make_uint4(0, 0, 0, 0);
+      // generic-proxy writes to a slot that the producer will refill through the async proxy (TMA): order them
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+
+      // ---- S = Q K^T: PPS/8 key tiles x 8 k-steps; one ldmatrix.x4 = the B fragments of 2 k-steps for one key tile
+      float sc[PPS / 8][4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          kf[2 * jj] = bf16lo(ku[jj]);
-          kf[2 * jj + 1] = bf16hi(ku[jj]);
-          vf[2 * jj] = bf16lo(vu[jj]);
-          vf[2 * jj + 1] = bf16hi(vu[jj]);
+      for (int t = 0; t < PPS / 8; ++t) {
+        sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
+        const uint32_t kaddr = smem_u32(kst) + (uint32_t)(t * 8 + (lane & 7)) * row_stride + (uint32_t)(lane >> 3) * 16;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(kaddr + k2 * 64, b0, b1, b2, b3);
+          mma_bf16_16816(sc[t], qa[2 * k2], b0, b1);
+          mma_bf16_16816(sc[t], qa[2 * k2 + 1], b2, b3);
         }
+      }
+      // ---- online softmax for row `row` (values c0, c1 of each key tile); keys >= nk are masked
+      float mx = m_run;
 #pragma unroll
-        for (int r = 0; r < REP; ++r) {
-          float d = 0.f;
+      for (int t = 0; t < PPS / 8; ++t) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) d = fmaf(qf[r][jj], kf[jj], d);
-          d += __shfl_xor_sync(0xffffffffu, d, 8);
-          d += __shfl_xor_sync(0xffffffffu, d, 4);
-          d += __shfl_xor_sync(0xffffffffu, d, 2);
-          d += __shfl_xor_sync(0xffffffffu, d, 1);
-          const float sc = valid ? d * scale : kMaskedScore;
-          const float mn = fmaxf(m[r], sc);
-          const float corr = exp2f((m[r] - mn) * kLog2e);
-          const float pe = exp2f((sc - mn) * kLog2e);
-          const float pr = valid ? pe : 0.f;
-          l[r] = l[r] * corr + pr;
+        for (int c = 0; c < 2; ++c) {
+          const int key = t * 8 + cq * 2 + c;
+          sc[t][c] = key < nk ? sc[t][c] * sl2 : kMaskedScore;
+          mx = fmaxf(mx, sc[t][c]);
+        }
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float corr = exp2f(m_run - mx);
+      m_run = mx;
+      l_run *= corr;
+      uint32_t pa[4] = {0u, 0u, 0u, 0u};  // P as the A fragment of one k16 step: a0 = keys 0-7, a2 = keys 8-15; rows + 8 stay zero
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) acc[r][jj] = fmaf(pr, vf[jj], acc[r][jj] * corr);
-          m[r] = mn;
+      for (int t = 0; t < PPS / 8; ++t) {
+        const float e0 = exp2f(sc[t][0] - mx), e1 = exp2f(sc[t][1] - mx);  // masked: exp2(-1e30) = 0
+        l_run += e0 + e1;
+        pa[2 * t] = pack_bf16x2(e0, e1);
+      }
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        o[n][0] *= corr;
+        o[n][1] *= corr;
+      }
+      // ---- O += P V: B = V^T fragments via ldmatrix.trans (rows = keys)
+      if constexpr (PPS == 16) {
+        const uint32_t vaddr = smem_u32(vst) + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * row_stride + (uint32_t)(lane >> 4) * 16;
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {  // dim tiles 2*n2, 2*n2+1
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(vaddr + n2 * 32, b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * n2], pa, b0, b1);
+          mma_bf16_16816(o[2 * n2 + 1], pa, b2, b3);
+        }
+      } else {  // 8 keys: the k16 step's upper half (keys 8-15) is zero on both operands
+        const uint32_t vaddr = smem_u32(vst) + (uint32_t)(lane & 7) * row_stride + (uint32_t)(lane >> 3) * 16;
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {  // dim tiles 4*n4 .. 4*n4+3
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(vaddr + n4 * 64, b0, b1, b2, b3);
+          mma_bf16_16816(o[4 * n4], pa, b0, 0u);
+          mma_bf16_16816(o[4 * n4 + 1], pa, b1, 0u);
+          mma_bf16_16816(o[4 * n4 + 2], pa, b2, 0u);
+          mma_bf16_16816(o[4 * n4 + 3], pa, b3, 0u);
         }
       }
     }
@@ -464,33 +548,16 @@ __device__ __forceinline__ void mk_attention_slice(const MkParams& p, const MkLa
   }
   rs.it += 2u * a.n_kvst;
   if (!has_head) return;
-  // merge the two half-warps and publish this slice's partial for the REP heads of kv head g
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);  // the 4 lanes of a row each summed their own columns
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (row >= REP) return;
+  // publish this slice's partial for query head g*REP + row; the merge works in the natural-exp domain: m / log2(e)
+  m_run *= 0.6931471805599453f;
   const int PSTRIDE = kHeadDim + 2;
-  float* mine = p.partial + ((int64_t)blockIdx.x * p.H + g * REP) * PSTRIDE;
+  float* mine = p.partial + ((int64_t)blockIdx.x * p.H + g * REP + row) * PSTRIDE;
 #pragma unroll
-  for (int r = 0; r < REP; ++r) {
-    const float mo = __shfl_xor_sync(0xffffffffu, m[r], 16);
-    const float lo = __shfl_xor_sync(0xffffffffu, l[r], 16);
-    const float mn = fmaxf(m[r], mo);
-    const float cs = (m[r] == -INFINITY) ? 0.f : exp2f((m[r] - mn) * kLog2e);
-    const float co = (mo == -INFINITY) ? 0.f : exp2f((mo - mn) * kLog2e);
-    const float lt = l[r] * cs + lo * co;
-    float out[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const float ao = __shfl_xor_sync(0xffffffffu, acc[r][jj], 16);
-      out[jj] = acc[r][jj] * cs + ao * co;
-    }
-    if (half == 0) {
-      float4* dst = reinterpret_cast<float4*>(mine + r * PSTRIDE + 2 + hl * 8);  // 8-byte aligned rows: use float2 stores
-      float2* d2 = reinterpret_cast<float2*>(dst);
-      d2[0] = make_float2(out[0], out[1]);
-      d2[1] = make_float2(out[2], out[3]);
-      d2[2] = make_float2(out[4], out[5]);
-      d2[3] = make_float2(out[6], out[7]);
-      if (hl == 0) *reinterpret_cast<float2*>(mine + r * PSTRIDE) = make_float2(mn, lt);
-    }
-  }
+  for (int n = 0; n < 16; ++n) *reinterpret_cast<float2*>(mine + 2 + n * 8 + cq * 2) = make_float2(o[n][0], o[n][1]);
+  if (cq == 0) *reinterpret_cast<float2*>(mine) = make_float2(m_run, l_run);
 }
 
 // ---- phase 2b: merge the slices.  Unit u = (query head, 32-dim quarter); warp w folds slices w, w+8, ... (all loads issued
@@ -503,13 +570,13 @@ __device__ __forceinline__ void mk_attention_combine(const MkParams& p, int W, i
   float* sm = scratch;  // [8 warps][34]: m, l, acc[32]
   for (int u = blockIdx.x; u < p.H * 4; u += gridDim.x) {
     const int h = u >> 2, q4 = u & 3;
-    float m = -INFINITY, l = 0.f, acc = 0.f;
+    float m = kMaskedScore, l = 0.f, acc = 0.f;
     for (int a0 = warp; a0 < a.n_slices; a0 += MK_CONSUMER_WARPS * MK_CMB_MAX) {
       float mt[MK_CMB_MAX], lt[MK_CMB_MAX], at[MK_CMB_MAX];
 #pragma unroll
       for (int i = 0; i < MK_CMB_MAX; ++i) {
         const int sl = a0 + i * MK_CONSUMER_WARPS;
-        mt[i] = -INFINITY;
+        mt[i] = kMaskedScore;
         lt[i] = at[i] = 0.f;
         if (sl < a.n_slices) {
           const float* pp = p.partial + ((int64_t)sl * p.H + h) * PSTRIDE;
@@ -519,15 +586,20 @@ __device__ __forceinline__ void mk_attention_combine(const MkParams& p, int W, i
           at[i] = __ldcg(pp + 2 + q4 * 32 + lane);
         }
       }
+      // two passes: the max first, then every slice's weight is independent (no sequential rescale chain)
+      float mn = m;
+#pragma unroll
+      for (int i = 0; i < MK_CMB_MAX; ++i) mn = fmaxf(mn, mt[i]);
+      const float c0 = exp2f((m - mn) * kLog2e);
+      l *= c0;
+      acc *= c0;
 #pragma unroll
       for (int i = 0; i < MK_CMB_MAX; ++i) {
-        const float mn = fmaxf(m, mt[i]);
-        const float c0 = (m == -INFINITY) ? 0.f : exp2f((m - mn) * kLog2e);
-        const float c1 = (mt[i] == -INFINITY) ? 0.f : exp2f((mt[i] - mn) * kLog2e);
-        l = l * c0 + lt[i] * c1;
-        acc = acc * c0 + at[i] * c1;
-        m = mn;
+        const float c1 = exp2f((mt[i] - mn) * kLog2e);
+        l = fmaf(lt[i], c1, l);
+        acc = fmaf(at[i], c1, acc);
       }
+      m = mn;
     }
     sm[warp * 34 + 2 + lane] = acc;
     if (lane == 0) {
@@ -536,14 +608,14 @@ __device__ __forceinline__ void mk_attention_combine(const MkParams& p, int W, i
     }
     consumer_sync();
     if (warp == 0) {
-      float mn = -INFINITY;
+      float mn = kMaskedScore;
 #pragma unroll
       for (int w = 0; w < MK_CONSUMER_WARPS; ++w) mn = fmaxf(mn, sm[w * 34]);
       float lt = 0.f, at = 0.f;
 #pragma unroll
       for (int w = 0; w < MK_CONSUMER_WARPS; ++w) {
         const float mw = sm[w * 34];
-        const float c = (mw == -INFINITY) ? 0.f : exp2f((mw - mn) * kLog2e);
+        const float c = exp2f((mw - mn) * kLog2e);
         lt += sm[w * 34 + 1] * c;
         at += sm[w * 34 + 2 + lane] * c;
       }
@@ -578,17 +650,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   rs.it = 0;
 
   if (tid >= MK_CONSUMERS) {
-    // ================= producer warp (weights and old KV rows never wait for activations) =================
-    const int lane = tid - MK_CONSUMERS;
-    for (int l = 0; l < p.n_layers; ++l) {
-      const MkLayer L = p.layers[l];
-      produce_matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, lane);
-      produce_kv(p, L, p.windows[l], ring, full, empty, p.n_stages, rs, lane);
-      produce_matrix(L.wo, p.dim, q_dim, ring, full, empty, p.n_stages, rs, lane);
-      produce_matrix(L.w13, 2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, lane);
-      produce_matrix(L.w2, p.dim, p.hidden, ring, full, empty, p.n_stages, rs, lane);
-    }
-    produce_matrix(p.w_out, p.vocab, p.dim, ring, full, empty, p.n_stages, rs, lane);
+    // ================= producer (one thread; weights and old K/V rows never wait for activations) =================
+    if (tid == MK_CONSUMERS) producer_main(p, ring, full, empty);
     return;
   }
 
@@ -627,17 +690,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       });
     }
     mk_stamp(p, tid, l, 2);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 0);
     mk_stamp(p, tid, l, 3);
 
     // ---- phase 2a: partial attention of my position slice;  2b: merge the slices ----
-    mk_attention_slice<REP>(p, L, W, ring, full, empty, p.n_stages, rs, tid);
+    if (attn_slice(p, W).pps == 16)
+      mk_attention_slice<REP, 16>(p, L, W, ring, full, empty, p.n_stages, rs, tid, l);
+    else
+      mk_attention_slice<REP, 8>(p, L, W, ring, full, empty, p.n_stages, rs, tid, l);
     mk_stamp(p, tid, l, 12);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 1);
     mk_stamp(p, tid, l, 13);
     mk_attention_combine(p, W, tid, reinterpret_cast<float*>(xs));
     mk_stamp(p, tid, l, 4);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 2);
     mk_stamp(p, tid, l, 5);
 
     // ---- phase 3: wo + residual ----
@@ -647,7 +713,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
     mk_stamp(p, tid, l, 6);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 3);
     mk_stamp(p, tid, l, 7);
 
     // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
@@ -657,7 +723,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
     });
     mk_stamp(p, tid, l, 8);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 4);
     mk_stamp(p, tid, l, 9);
 
     // ---- phase 5: down + residual ----
@@ -667,7 +733,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
     mk_stamp(p, tid, l, 10);
-    grid_barrier(p, tid, epoch);
+    grid_barrier(p, tid, epoch, l, 5);
     mk_stamp(p, tid, l, 11);
   }
 

@@ -23,12 +23,16 @@ for _ in range(3):
     model.decode_static(tok, cache)
 buf = torch.zeros(8 * L * 16, dtype=torch.int64, device="cuda")
 _abi.set_decode_timeline(buf)
+sm_count = _abi.device_info()[0]
+bbuf = torch.zeros(sm_count * L * 6 * 2, dtype=torch.int64, device="cuda")
+_abi.set_barrier_timeline(bbuf)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 model.decode_static(tok, cache)
 e1.record()
 torch.cuda.synchronize()
 _abi.set_decode_timeline(None)
+_abi.set_barrier_timeline(None)
 t = buf.cpu().view(8, L, 16).double() / 1000.0  # us; 8 sampled CTAs (0, 21, ..., 147)
 names = ["stage_x+norm", "QKV gemv", "barrier1", "attention", "barrier2", "stage+WO gemv", "barrier3", "stage+GATEUP", "barrier4",
          "stage+DOWN", "barrier5"]
@@ -42,10 +46,20 @@ lea = t[:, 1:, [3, 5, 7, 9, 11]]  # leave times
 skew = (arr.max(0).values - arr.min(0).values).median(0).values
 lat = (lea.min(0).values - arr.max(0).values).median(0).values
 a = t[:6, 1:]  # active sampled CTAs
-sub = torch.stack([a[:, :, 12] - a[:, :, 3], a[:, :, 13] - a[:, :, 12], a[:, :, 4] - a[:, :, 13]], -1).median(1).values
-print("  inside attention (us; slice partial | mid barrier | slice merge), per sampled CTA:")
+sub = torch.stack([a[:, :, 14] - a[:, :, 3], a[:, :, 15] - a[:, :, 3], a[:, :, 12] - a[:, :, 3], a[:, :, 13] - a[:, :, 12], a[:, :, 4] - a[:, :, 13]], -1).median(1).values
+print("  inside attention (us; first KV stage ready | last KV stage ready | slice partial done (all since phase start) | mid barrier | slice merge):")
 for row in sub.tolist():
     print("     ", [round(x, 2) for x in row])
 print("  barrier arrival skew across sampled CTAs (us):", [round(x, 2) for x in skew.tolist()])
 print("  barrier latency last-arrival -> first-leave (us):", [round(x, 2) for x in lat.tolist()])
 print(f"  layer total (cta0) {(t[0, 1:, 11] - t[0, 1:, 0]).median().item():8.2f}   (ideal HBM time per layer at 6583 GB/s: {(436.2e6 + 16.8e6) / 6583.5e3:.1f} us)")
+
+bt = bbuf.cpu().view(sm_count, L, 6, 2).double() / 1000.0
+arr, lea = bt[:, 1:, :, 0], bt[:, 1:, :, 1]
+print("  ALL CTAs, per barrier (median over layers): arrival skew (last - first arrive) | latency (first leave - last arrive) | leave spread")
+for b, nm in enumerate(["after QKV", "after slice partial", "after slice merge", "after WO", "after GATEUP", "after DOWN"]):
+    skew = (arr[:, :, b].max(0).values - arr[:, :, b].min(0).values).median().item()
+    lat = (lea[:, :, b].min(0).values - arr[:, :, b].max(0).values).median().item()
+    spread = (lea[:, :, b].max(0).values - lea[:, :, b].min(0).values).median().item()
+    slow = arr[:, :, b].argmax(0).mode().values.item()
+    print(f"    {nm:20s} skew {skew:6.2f}   latency {lat:6.2f}   leave spread {spread:6.2f}   (most often last: CTA {slow})")
