@@ -4,6 +4,7 @@
 #include "decode_megakernel.cuh"
 #include "elementwise.cuh"
 #include "gemm_mma.cuh"
+#include "gemm_tcgen05.cuh"
 #include "skinny_linear.cuh"
 
 namespace mb200 {
@@ -53,6 +54,7 @@ static int run_linear(const void* x, const void* norm_w, const void* w, const Ep
   g.N = (int)N;
   g.K = (int)K;
   g.epi = epi;
+  if (tcgen05_gemm_eligible(T, N, K)) return launch_gemm_tcgen05<MODE>(g, st);
   return launch_gemm_mma<MODE>(g, st);
 }
 }  // namespace mb200

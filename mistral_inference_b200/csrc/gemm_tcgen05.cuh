@@ -1,0 +1,250 @@
+// C[T, N] = A[T, K] * W[N, K]^T on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed.
+//
+// Roofline: tensor pipe (2*T*N*K flops).  Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled [128 x 64] A tile + [256 x 64] W tile per stage) -> 4-stage ring
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M = 128, N = 256, K = 16 x 4 per stage); tcgen05.commit
+//            releases the shared-memory stage and, after the last k-block, publishes the accumulator
+//   warps 2-5 epilogue: tcgen05.ld the 128 x 256 fp32 accumulator out of TMEM (two buffers of 256 columns, so the MMAs of the
+//            next tile overlap this one's epilogue) and run the same pair epilogues as every other linear (bf16 rounding,
+//            RoPE + ring scatter, SiLU*mul, residual add, fp32 logits)
+// Both operands are K-major ([rows, K] row-major): the canonical TN GEMM, no transposes anywhere.
+// Tiles are walked m-fastest so that the ~32 CTAs that share a W tile run together and hit it in L2.
+#pragma once
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "decode_megakernel.cuh"  // mbarrier helpers with the watchdog
+#include "epilogue.cuh"
+#include "gemm_mma.cuh"
+
+namespace mb200 {
+
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2, TG_B_BYTES = TG_BN * TG_BK * 2;
+constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TG_TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
+
+struct TcGemmParams {
+  int T, N, K;
+  EpiParams epi;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major, 128B-swizzled tile whose rows are 64 bf16 = 128 bytes:
+// 8-row swizzle atoms of 1024 B (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B).  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kUmmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TG_BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+
+template <int MODE>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 wants 1024-B tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  uint64_t* empty = full + TG_STAGES;
+  uint64_t* tmem_full = empty + TG_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.T + TG_BM - 1) / TG_BM, num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TG_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TG_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * TG_BM, n0 = (tile / num_m) * TG_BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const uint32_t s = it % TG_STAGES, par = (it / TG_STAGES) & 1;
+          mbar_wait(&empty[s], par ^ 1, 11, it);
+          mbar_arrive_expect_tx(&full[s], TG_STAGE_BYTES);
+          uint8_t* sa = smem + s * TG_STAGE_BYTES;
+          tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, m0);
+          tma_load_2d(sa + TG_A_BYTES, &map_w, &full[s], kb * TG_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+        const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_par ^ 1, 12, acc_it);  // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TG_BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const uint32_t s = it % TG_STAGES, par = (it / TG_STAGES) & 1;
+          mbar_wait(&full[s], par, 13, it);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * TG_STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + TG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k)  // +32 bytes (= 2 in 16-byte units) per K = 16 step inside the 128-byte swizzled row
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kUmmaIdesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =================
+    const int lane_base = (warp & 3) * 32;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+      const int m0 = (tile % num_m) * TG_BM, n0 = (tile / num_m) * TG_BN;
+      const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_par, 14, acc_it);
+      tc_fence_after();
+      const int t = m0 + lane_base + lane;
+#pragma unroll 1
+      for (int c = 0; c < TG_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN + c * 32, v);
+        if (t < p.T) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) epi_pair<MODE>(p.epi, t, n0 + c * 32 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TG_TMEM_COLS);
+}
+
+// ---- host: tensor maps (driver API through the runtime's entry-point lookup, no libcuda link dependency) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// [rows, K] bf16 row-major, box = [box_rows x 64] elements, 128-byte swizzle, out-of-range rows read as zero
+inline int make_tensor_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return fail(MB200_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TG_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld", (int)r, (long long)rows, (long long)K);
+  return MB200_OK;
+}
+
+// MB200_GEMM=mma forces the mma.sync kernel (A/B comparisons, debugging)
+inline bool tcgen05_gemm_eligible(int64_t T, int64_t N, int64_t K) {
+  static int forced_mma = -1;
+  if (forced_mma < 0) {
+    const char* e = getenv("MB200_GEMM");
+    forced_mma = (e != nullptr && e[0] == 'm') ? 1 : 0;
+  }
+  return !forced_mma && T >= TG_BM && N % TG_BN == 0 && K % TG_BK == 0;
+}
+
+template <int MODE>
+int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
+  CUtensorMap map_a, map_w;
+  int rc = make_tensor_map_2d(&map_a, g.a, g.T, g.K, TG_BM);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, TG_BN);
+  if (rc) return rc;
+  TcGemmParams p;
+  p.T = g.T;
+  p.N = g.N;
+  p.K = g.K;
+  p.epi = g.epi;
+  int dev = 0, sms = 0;
+  MB_CHECK_CUDA(cudaGetDevice(&dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = ceil_div(g.T, TG_BM) * (g.N / TG_BN);
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  gemm_tcgen05_kernel<MODE><<<tiles < sms ? tiles : sms, TG_THREADS, TG_SMEM, stream>>>(map_a, map_w, p);
+  MB_CHECK_LAUNCH("gemm_tcgen05_kernel");
+  return MB200_OK;
+}
+
+}  // namespace mb200
