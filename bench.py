@@ -161,7 +161,16 @@ def run_ours(a, rank: int, world: int):
     del logits
 
     # ---- decode: device-resident loop (value) ----
-    def step(t):
+    kern_ev = []  # (start, end) CUDA events around the hot-path launch of each timed step (the decode megakernel)
+
+    def step(t, timed=False):
+        if timed:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            lg = model.decode_static(t, cache)
+            a1.record()
+            kern_ev.append((a0, a1))
+            return lg.argmax(-1)
         return model.decode_static(t, cache).argmax(-1)
 
     for _ in range(max(a.warmup, 3)):
@@ -172,10 +181,11 @@ def run_ours(a, rank: int, world: int):
     with ClockSampler(dev_index) as clocks:
         e0.record()
         for _ in range(a.steps):
-            tok = step(tok)
+            tok = step(tok, timed=True)
         e1.record()
         torch.cuda.synchronize()
     dec_ms = e0.elapsed_time(e1)
+    kern_us = 1000.0 * sum(x.elapsed_time(y) for x, y in kern_ev) / len(kern_ev)
     if world > 1:
         t = torch.tensor([dec_ms], device=model.device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -216,42 +226,31 @@ def run_ours(a, rank: int, world: int):
         e2e_s = float(t.item())
     e2e_val = world * a.batch * a.steps / e2e_s
 
-    # ---- dominant kernel alone: fused RMSNorm + gate/up GEMV + SiLU*mul, cycling through all layers' weights ----
+    # ---- roofline of the dominant kernel ----
     roof = None
     if rank == 0:
-        ws = model.workspace(a.batch)
-        x = torch.randn(a.batch, p["dim"], device=model.device).to(torch.bfloat16)
-        g = torch.empty(a.batch, p["hidden_dim"], device=model.device, dtype=torch.bfloat16)
-        blocks = list(model.layers.values())
-        if p.get("moe") is None:
-            def dom(i):
-                b = blocks[i % L]
-                _abi.ffn_gateup(x, b.ffn_norm.weight, b.feed_forward.w13, g, p["norm_eps"], ws)
-            for i in range(L):
-                dom(i)
-            torch.cuda.synchronize()
-            reps = max(L, 4 * L if L < 32 else 2 * L)
-            e0.record()
-            for i in range(reps):
-                dom(i)
-            e1.record()
-            torch.cuda.synchronize()
-            dom_us = e0.elapsed_time(e1) * 1000.0 / reps
-            dom_bytes = 2 * p["hidden_dim"] * p["dim"] * 2
-            achieved = dom_bytes / (dom_us * 1e-6) / 1e9
-            traffic = None
-            tf = REPO / "profiles" / "dominant_kernel_traffic.json"
-            if tf.exists():
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-            roof = {"bound": "hbm", "kernel": "skinny_linear_kernel<1,SWIGLU,NORM> (fused RMSNorm + gate/up GEMV + SiLU*mul)",
+        megakernel = model._megakernel_ok(a.batch)
+        traffic = None
+        tf = REPO / "profiles" / "dominant_kernel_traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        if megakernel:
+            # one launch = one whole decode step: algorithmic bytes per launch = bytes per step; duration = CUDA events
+            # around each launch in the timed loop (same stream), averaged
+            achieved = step_bytes / (kern_us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": "decode_megakernel<4> (one persistent cooperative kernel per token: all layers + lm head)",
                     "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-                    "traffic": traffic, "bytes_per_launch": dom_bytes, "us_per_launch": round(dom_us, 2), "peak_source": peaks["source"],
-                    "timing": "CUDA events around back-to-back launches cycling over all layers' weights (> L2)"}
+                    "traffic": traffic, "bytes_per_launch": step_bytes, "us_per_launch": round(kern_us, 2), "peak_source": peaks["source"],
+                    "timing": "CUDA events around every launch inside the timed decode loop (launch stream), mean of %d" % len(kern_ev)}
+        else:
+            roof = {"bound": "hbm", "kernel": "per-op decode path (CUDA graph of skinny_linear / attn_decode kernels)", "achieved": None,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
 
     cpu = cpu_baseline(a, p, bounded_seconds=20.0) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     if rank != 0:
         return None
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    prefill_kernels = "gemm_tcgen05_kernel (tcgen05.mma/TMEM/TMA) + attn_prefill_kernel (mma.sync flash) + rmsnorm/kv_ring_write"
     return {
         "metric": "decode tokens/sec (bf16, batch=1, seq=4k) [+ prefill TFLOPS, both vs roofline]",
         "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -261,17 +260,18 @@ def run_ours(a, rank: int, world: int):
                                f"batch={a.batch} {a.prefill}-token prefill then decode at kv_len~{kv_len}",
                    "parallelism": "replicas only" if world > 1 else "single GPU", "global_batch": a.batch * world, "seq_len": a.prefill,
                    "l2": "inputs larger than L2 (14.2 GB of weights streamed per step vs 126 MB L2)",
-                   "decode_launch": "CUDA graph replay of the per-token kernel sequence",
+                   "decode_launch": "one persistent cooperative kernel per token (decode_megakernel)" if model._megakernel_ok(a.batch) else "CUDA graph replay of the per-op kernel sequence",
                    "valid": a.layers in (None, 0)},
         "e2e": {"value": round(e2e_val, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8 * a.batch, "d2h_bytes_per_step": 8 * a.batch,
                 "api": "Transformer.forward(host token -> pinned H2D, seqlens=[1], cache) + argmax/logprob D2H, synchronised every step"},
-        "gpu_launches": a.steps * (5 * L + 1),
+        "gpu_launches": a.steps * (1 if model._megakernel_ok(a.batch) else 5 * L + 1),
         "clocks": clocks.summary(),
         "roofline": roof,
         "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes, "achieved": round(step_gbs, 1), "peak": peaks["hbm_gbs"],
                           "unit": "GB/s", "frac": round(step_gbs / peaks["hbm_gbs"], 4), "peak_source": peaks["source"]},
         "prefill": {"tokens": a.prefill * a.batch, "ms": round(prefill_ms, 2), "tflops": round(pf / prefill_ms / 1e9, 1),
-                    "frac_of_burst_peak": round(pf / prefill_ms / 1e9 / peaks["bf16_tflops"], 4), "algorithmic_flops": pf},
+                    "frac_of_burst_peak": round(pf / prefill_ms / 1e9 / peaks["bf16_tflops"], 4), "algorithmic_flops": pf,
+                    "bound": "tensor", "peak_tflops": peaks["bf16_tflops"], "kernels": prefill_kernels},
         "cpu_baseline": cpu,
     }
 
@@ -284,7 +284,8 @@ def cpu_baseline(a, p: dict, bounded_seconds: float, steps: int = 0):
     would need minutes just to materialise."""
     from oracle import restatement as R
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
     n = min(p["n_layers"], 4)
     ps = dict(p, n_layers=n)
     moe = p.get("moe") or {}
@@ -305,6 +306,20 @@ def cpu_baseline(a, p: dict, bounded_seconds: float, steps: int = 0):
     t_all = time.perf_counter()
     with torch.inference_mode():
         om.forward(tok, [1] * a.batch, cache)  # warm-up
+        # batch-1 bf16 matvecs do not scale to every core of a big host (128 threads measured 20x slower than 8): use the
+        # thread count that is fastest for this workload, and report it
+        best = (None, float("inf"))
+        for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+            torch.set_num_threads(nt)
+            om.hidden(tok, [1] * a.batch, cache, last_stage=False)
+            cache.kv_seqlens = [a.prefill] * a.batch
+            t0 = time.perf_counter()
+            om.hidden(tok, [1] * a.batch, cache, last_stage=False)
+            dt = time.perf_counter() - t0
+            cache.kv_seqlens = [a.prefill] * a.batch
+            if dt < best[1]:
+                best = (nt, dt)
+        torch.set_num_threads(best[0])
         while True:
             t0 = time.perf_counter()
             h = om.hidden(tok, [1] * a.batch, cache, last_stage=False)
@@ -312,12 +327,14 @@ def cpu_baseline(a, p: dict, bounded_seconds: float, steps: int = 0):
             torch.nn.functional.linear(R.rms_norm(h, w["norm.weight"], p["norm_eps"]), w["output.weight"]).float()
             t2 = time.perf_counter()
             times.append((t1 - t0, t2 - t1))
+            cache.kv_seqlens = [a.prefill] * a.batch  # stay at the same context length
             if (steps and len(times) >= steps) or (not steps and (time.perf_counter() - t_all > bounded_seconds or len(times) >= 50)):
                 break
     t_layers = statistics.median(t[0] for t in times) / n
     t_head = statistics.median(t[1] for t in times)
     s_per_tok = t_layers * p["n_layers"] + t_head
     return {"value": round(a.batch / s_per_tok, 4), "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": ncpu,
             "sample": f"{len(times)} decode steps of a {n}-layer slice of {a.model} (real layer shapes, kv ring full at W={W}) + final norm + "
                       f"lm head, per-layer median x {p['n_layers']} layers (labelled extrapolation)",
             "ms_per_layer": round(t_layers * 1e3, 3), "ms_lm_head": round(t_head * 1e3, 3)}
