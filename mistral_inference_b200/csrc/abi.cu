@@ -289,8 +289,16 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   // global scratch: header words + activations + per-slice attention partials
   uint8_t* ws = (uint8_t*)workspace;
   p.attn_counters = (int*)(ws + 8192);
-  p.bar_flags = (unsigned*)(ws + 16384);  // sms x 32 B
-  MB_CHECK_ARG((size_t)sms * 32 <= kWsHeader - 16384, "decode_step: too many SMs for the barrier flag block");
+  p.bar_flags = (unsigned*)(ws + 16384);
+  {
+    // the barrier counter lives in the caller's workspace; its value is tracked per workspace on the host (stream-ordered launches)
+    static std::mutex mu;
+    static std::unordered_map<void*, unsigned> base;
+    std::lock_guard<std::mutex> lk(mu);
+    unsigned& b = base[(void*)ws];
+    p.bar_base = b;
+    b += (unsigned)(6 * n_layers) * (unsigned)sms;  // six grid barriers per layer
+  }
   MB_CHECK_ARG((size_t)n_kv_heads * sizeof(int) <= 4096, "decode_step: too many kv heads");
   size_t off = kWsHeader;
   auto take = [&](size_t bytes) { uint8_t* r = ws + off; off += align256(bytes); return r; };
