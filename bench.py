@@ -105,6 +105,20 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in ok if r[2].replace(".", "").isdigit()), "samples": len(ok), "reasons": reasons}
 
 
+def max_over_ranks(value: float, world: int, device) -> float:
+    """Timing rule for N > 1: every rank times its own replica on the device, the job's time is the MAX over ranks."""
+    if world <= 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_tokens_per_s(world: int, batch: int, steps: int, elapsed_ms: float) -> float:
+    """Replicas only (dense models fit one GPU): every rank decodes `batch` sequences for `steps` steps, weak scaling."""
+    return world * batch * steps * 1000.0 / elapsed_ms
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def build_gpu_model(p: dict, max_batch: int, seed: int = 0):
     import mistral_inference_b200 as mi
@@ -186,12 +200,9 @@ def run_ours(a, rank: int, world: int):
         torch.cuda.synchronize()
     dec_ms = e0.elapsed_time(e1)
     kern_us = 1000.0 * sum(x.elapsed_time(y) for x, y in kern_ev) / len(kern_ev)
-    if world > 1:
-        t = torch.tensor([dec_ms], device=model.device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        dec_ms = float(t.item())
+    dec_ms = max_over_ranks(dec_ms, world, model.device)
     ms_per_step = dec_ms / a.steps
-    value = world * a.batch * 1000.0 / ms_per_step
+    value = whole_job_tokens_per_s(world, a.batch, a.steps, dec_ms)
     kv_len = min(W, a.prefill + a.warmup + a.steps // 2)
     step_bytes = decode_bytes_per_step(p, kv_len, a.batch)
     peaks = measured_peaks()
@@ -219,12 +230,8 @@ def run_ours(a, rank: int, world: int):
     for _ in range(a.steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=model.device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = world * a.batch * a.steps / e2e_s
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, model.device)
+    e2e_val = whole_job_tokens_per_s(world, a.batch, a.steps, e2e_s * 1000.0)
 
     # ---- roofline of the dominant kernel ----
     roof = None

@@ -1,4 +1,6 @@
 // libmb200.so -- the C ABI declared in include/mistral_b200.h.  Argument checking + kernel dispatch only.
+#include <cstdlib>
+
 #include "attn_decode.cuh"
 #include "attn_prefill.cuh"
 #include "decode_megakernel.cuh"
@@ -282,6 +284,14 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   MB_CHECK_ARG(n_stages > MK_CONSUMER_WARPS, "decode_step: not enough shared memory for the weight ring (%d stages)", n_stages);
   p.n_stages = n_stages;
   p.xs_bytes = (int)xs_bytes;
+  {
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("MB200_MK_INFLIGHT");
+      cap = e ? atoi(e) : 5;  // B200 sweep (7B): 3 -> 3.02 ms/token, 4 -> 2.87, 6 -> 2.87, 8 -> 2.89, uncapped -> 2.92
+    }
+    p.inflight_cap = cap < 2 ? 2 : (cap > 8 ? 8 : cap);
+  }
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
 
   MB_CHECK_ARG(n_kv_heads <= MK_CONSUMER_WARPS, "decode_step: n_kv_heads=%lld > %d (one consumer warp per kv head)", (long long)n_kv_heads,
@@ -297,7 +307,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
     std::lock_guard<std::mutex> lk(mu);
     unsigned& b = base[(void*)ws];
     p.bar_base = b;
-    b += (unsigned)(6 * n_layers) * (unsigned)sms;  // six grid barriers per layer
+    b += (unsigned)(6 * n_layers);  // six grid barriers per layer
   }
   MB_CHECK_ARG((size_t)n_kv_heads * sizeof(int) <= 4096, "decode_step: too many kv heads");
   size_t off = kWsHeader;

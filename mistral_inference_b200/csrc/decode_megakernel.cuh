@@ -32,7 +32,8 @@ namespace mb200 {
 
 constexpr int MK_CONSUMER_WARPS = 8;
 constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
-constexpr int MK_THREADS = MK_CONSUMERS + 32;  // + producer warp
+constexpr int MK_PRODUCER_WARPS = 2;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
+constexpr int MK_THREADS = MK_CONSUMERS + 32 * MK_PRODUCER_WARPS;
 constexpr int MK_WEIGHT_STAGE_BYTES = 16 * 1024;   // a weight stage: 2 rows x KC elements x 2 B
 constexpr int MK_MAX_KC = MK_WEIGHT_STAGE_BYTES / 4;  // elements per row chunk
 constexpr int MK_KV_PAD = 16;                      // K/V position rows are laid out with a 16-byte pad (ldmatrix bank spread)
@@ -66,9 +67,10 @@ struct MkParams {
   int dim, hidden, H, KV, vocab;
   float eps;
   int n_stages, xs_bytes;
+  int inflight_cap;  // max ring stages with outstanding bulk copies (< n_stages)
   // scratch (global)
   unsigned* bar_flags;  // grid barrier counter (monotonic, never reset)
-  unsigned bar_base;    // its value when this launch starts = (barriers completed so far) x gridDim
+  unsigned bar_base;    // number of barriers completed before this launch (host-tracked)
   int* attn_counters;   // [KV]
   bf16* xbuf;           // [2][dim] residual stream ping-pong
   bf16* hbuf;           // [dim]
@@ -151,10 +153,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // x gridDim), so nothing has to be read or reset on the device.
 // (Measured alternatives on 148 CTAs: counter + generation word with fences 5 us; one flag per CTA polled by 148 threads of
 // every CTA 1.5 us when arrivals are spread out but 4-5 us when all CTAs arrive together -- 22 K simultaneous polls.)
-__device__ __forceinline__ unsigned atom_add_release_u32(unsigned* p, unsigned v) {
-  unsigned old;
-  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
+// Arrivals are spread over MK_BAR_WORDS counters on different 128-byte lines (CTA c -> word c % 8): when all CTAs arrive
+// within ~0.5 us (after the short wo / down phases) 148 same-address atomics serialise at one L2 slice (~3 us measured).
+constexpr int MK_BAR_WORDS = 8;
+__device__ __forceinline__ void red_add_release_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void bar_stamp(const MkParams& p, int tid, int layer, int which, int leave) {
   if (p.prof_bar != nullptr && tid == 0 && layer >= 0) {
@@ -164,15 +167,19 @@ __device__ __forceinline__ void bar_stamp(const MkParams& p, int tid, int layer,
   }
 }
 __device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch, int layer = -1, int which = 0) {
-  epoch += gridDim.x;  // the counter value that completes this barrier
+  ++epoch;  // number of barriers completed once this one is
   bar_stamp(p, tid, layer, which, 0);
   consumer_sync();  // every consumer thread's global writes of this phase happen-before thread 0's release below
-  if (tid == 0) {
-    atom_add_release_u32(p.bar_flags, 1u);
+  if (tid == 0) red_add_release_u32(p.bar_flags + (blockIdx.x % MK_BAR_WORDS) * 32, 1u);
+  if (tid < MK_BAR_WORDS) {
+    // word j collects the CTAs with c % 8 == j: n_j of them per barrier
+    const unsigned n_j = (gridDim.x - tid + MK_BAR_WORDS - 1) / MK_BAR_WORDS;
+    const unsigned target = epoch * n_j;
     unsigned spins = 0;
-    while ((int)(ld_acquire_u32(p.bar_flags) - epoch) < 0) {
+    while ((int)(ld_acquire_u32(p.bar_flags + tid * 32) - target) < 0) {
       if (++spins == MB200_WATCHDOG_SPINS) {
-        printf("[mb200 watchdog] block %d stuck in grid barrier target=%u counter=%u\n", (int)blockIdx.x, epoch, ld_acquire_u32(p.bar_flags));
+        printf("[mb200 watchdog] block %d stuck in grid barrier word %d target=%u counter=%u\n", (int)blockIdx.x, tid, target,
+               ld_acquire_u32(p.bar_flags + tid * 32));
         __trap();
       }
     }
@@ -244,13 +251,40 @@ struct Producer {
   uint32_t it;
   uint64_t policy;  // L2 evict-first: weights and old K/V rows are read exactly once per token
 
+  // In-flight cap: stage `it` is only issued once stage it - cap has LANDED.  All n_stages slots still buffer data through the
+  // phase boundaries, but the SM never has more than `cap` stages of read requests queued: right after a short phase the
+  // consumers have drained the whole ring, and an uncapped producer then fires 12 x 16 KB at once -- the grid barrier's own
+  // atomic / polls queue behind that burst in the SM's memory request path (measured: barrier latency 4 us after the wo
+  // phase vs 1.5 us in steady state).  The bandwidth-delay product of one SM's HBM share is only ~3 stages.
+  int cap;
+  int me, n_prod;          // this producer issues the stages with it % n_prod == me
+  uint32_t slot, par;      // ring slot / parity of stage `it`, kept incrementally (no division in the issue loop)
+  uint32_t cslot, cpar;    // same for stage it - cap
+
+  __device__ __forceinline__ void advance() {
+    ++it;
+    if (++slot == (uint32_t)n_stages) {
+      slot = 0;
+      par ^= 1;
+    }
+    if (it > (uint32_t)cap && ++cslot == (uint32_t)n_stages) {
+      cslot = 0;
+      cpar ^= 1;
+    }
+  }
+  // returns the slot's buffer (and its full barrier, armed for `bytes`) or nullptr when the stage belongs to another producer
   __device__ __forceinline__ uint8_t* acquire(uint32_t bytes, uint64_t*& bar) {
-    const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
+    if ((int)(it % (uint32_t)n_prod) != me) {
+      advance();
+      return nullptr;
+    }
+    if (it >= (uint32_t)cap) mbar_wait(&full[cslot], cpar, 7, it);  // stage it - cap has landed (its slot cannot have been refilled yet)
     mbar_wait(&empty[slot], par ^ 1, 1, it);
     bar = &full[slot];
     mbar_arrive_expect_tx(bar, bytes);
-    ++it;
-    return ring + (size_t)slot * MK_STAGE_BYTES;
+    uint8_t* dst = ring + (size_t)slot * MK_STAGE_BYTES;
+    advance();
+    return dst;
   }
 
   // this CTA's slice of one [N, K] weight matrix, in the stage order consume_matrix expects
@@ -264,6 +298,7 @@ struct Producer {
           const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
           uint64_t* bar;
           uint8_t* dst = acquire(2 * row_bytes, bar);
+          if (dst == nullptr) continue;
           if (c.nch == 1) {
             bulk_g2s_hint(dst, r0, 2 * row_bytes, bar, policy);  // the two rows are contiguous
           } else {
@@ -290,6 +325,7 @@ struct Producer {
       for (int kv = 0; kv < 2; ++kv) {
         uint64_t* bar;
         uint8_t* dst = acquire((uint32_t)rows * row_bytes, bar);
+        if (dst == nullptr) continue;
         const bf16* src = (kv ? vbase : kbase) + (int64_t)k0 * row_elems;
         for (int r = 0; r < rows; ++r) bulk_g2s_hint(dst + r * (row_bytes + MK_KV_PAD), src + (int64_t)r * row_elems, row_bytes, bar, policy);
       }
@@ -297,13 +333,17 @@ struct Producer {
   }
 };
 
-__device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+__device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int me) {
   Producer pr;
   pr.ring = ring;
   pr.full = full;
   pr.empty = empty;
   pr.n_stages = p.n_stages;
   pr.it = 0;
+  pr.cap = p.inflight_cap;
+  pr.me = me;
+  pr.n_prod = MK_PRODUCER_WARPS;
+  pr.slot = pr.par = pr.cslot = pr.cpar = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.policy));
   const int q_dim = p.H * kHeadDim, kv_dim = p.KV * kHeadDim;
   for (int l = 0; l < p.n_layers; ++l) {
@@ -656,13 +696,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   rs.it = 0;
 
   if (tid >= MK_CONSUMERS) {
-    // ================= producer (one thread; weights and old K/V rows never wait for activations) =================
-    if (tid == MK_CONSUMERS) producer_main(p, ring, full, empty);
+    // ================= producers (one thread per producer warp; weights and old K/V rows never wait for activations) =================
+    if ((tid & 31) == 0) producer_main(p, ring, full, empty, (tid - MK_CONSUMERS) >> 5);
     return;
   }
 
   // ================= consumer warps =================
-  unsigned epoch = p.bar_base;  // counter value when this launch started (host-tracked)
+  unsigned epoch = p.bar_base;  // barriers completed so far
   const int64_t token = *p.token;
   for (int l = 0; l < p.n_layers; ++l) {
     const MkLayer L = p.layers[l];

@@ -63,3 +63,13 @@ for b, nm in enumerate(["after QKV", "after slice partial", "after slice merge",
     spread = (lea[:, :, b].max(0).values - lea[:, :, b].min(0).values).median().item()
     slow = arr[:, :, b].argmax(0).mode().values.item()
     print(f"    {nm:20s} skew {skew:6.2f}   latency {lat:6.2f}   leave spread {spread:6.2f}   (most often last: CTA {slow})")
+
+# per-CTA arrival pattern at the gate/up barrier (index 4) and the wo barrier (3), layer 3
+for b, nm in [(4, "after GATEUP"), (3, "after WO"), (5, "after DOWN")]:
+    arrv = bt[:, 3, b, 0]
+    rel = arrv - arrv.min()
+    order = rel.argsort()
+    print(f"  {nm}: arrival offsets (us) percentiles 10/50/90/100: {rel.quantile(0.1):.2f} {rel.quantile(0.5):.2f} {rel.quantile(0.9):.2f} {rel.max():.2f};"
+          f" earliest CTAs {order[:8].tolist()} latest CTAs {order[-12:].tolist()}")
+    lv = bt[:, 3, b, 1]
+    print(f"      leave - last arrive per CTA: min {(lv - arrv.max()).min():.2f} median {(lv - arrv.max()).median():.2f} max {(lv - arrv.max()).max():.2f}")
