@@ -166,15 +166,25 @@ __device__ __forceinline__ void bar_stamp(const MkParams& p, int tid, int layer,
     p.prof_bar[(((int64_t)blockIdx.x * p.n_layers + layer) * 6 + which) * 2 + leave] = t;
   }
 }
-__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch, int layer = -1, int which = 0) {
+// Word j collects the arrivals of a CONTIGUOUS range of CTAs (c -> c * 8 / gridDim), which lets a phase whose input chunk was
+// produced by a known CTA range wait for just that range (see the down projection).
+__device__ __forceinline__ int bar_word_of(int cta) { return (cta * MK_BAR_WORDS) / (int)gridDim.x; }
+__device__ __forceinline__ unsigned bar_word_count(int j) {  // number of CTAs mapping to word j
+  const int G = (int)gridDim.x;
+  // first cta with c*8/G >= j  is ceil(j*G/8)
+  const int lo = (j * G + MK_BAR_WORDS - 1) / MK_BAR_WORDS, hi = ((j + 1) * G + MK_BAR_WORDS - 1) / MK_BAR_WORDS;
+  return (unsigned)(hi - lo);
+}
+__device__ __forceinline__ void grid_arrive(const MkParams& p, int tid, unsigned& epoch, int layer = -1, int which = 0) {
   ++epoch;  // number of barriers completed once this one is
   bar_stamp(p, tid, layer, which, 0);
   consumer_sync();  // every consumer thread's global writes of this phase happen-before thread 0's release below
-  if (tid == 0) red_add_release_u32(p.bar_flags + (blockIdx.x % MK_BAR_WORDS) * 32, 1u);
-  if (tid < MK_BAR_WORDS) {
-    // word j collects the CTAs with c % 8 == j: n_j of them per barrier
-    const unsigned n_j = (gridDim.x - tid + MK_BAR_WORDS - 1) / MK_BAR_WORDS;
-    const unsigned target = epoch * n_j;
+  if (tid == 0) red_add_release_u32(p.bar_flags + bar_word_of(blockIdx.x) * 32, 1u);
+}
+// wait until every CTA in words [w_lo, w_hi] has arrived at barrier number `epoch`
+__device__ __forceinline__ void grid_wait(const MkParams& p, int tid, unsigned epoch, int w_lo, int w_hi) {
+  if (tid >= w_lo && tid <= w_hi) {
+    const unsigned target = epoch * bar_word_count(tid);
     unsigned spins = 0;
     while ((int)(ld_acquire_u32(p.bar_flags + tid * 32) - target) < 0) {
       if (++spins == MB200_WATCHDOG_SPINS) {
@@ -185,6 +195,10 @@ __device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigne
     }
   }
   consumer_sync();
+}
+__device__ __forceinline__ void grid_barrier(const MkParams& p, int tid, unsigned& epoch, int layer = -1, int which = 0) {
+  grid_arrive(p, tid, epoch, layer, which);
+  grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
   bar_stamp(p, tid, layer, which, 1);
 }
 
@@ -364,19 +378,22 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
 // `pre(n)` runs on the finishing lane BEFORE the pair's stages are consumed and its result is handed to `epi`: loads the
 // epilogue needs (the residual) are then off the critical path of the phase's last pair (an L2 round trip right before the
 // barrier's release store: measured 3.2-4.2 us barrier latency after wo / down vs 1.75 us after gate/up, which loads nothing).
-template <class Pre, class Epi>
+// `ready(ch)` is called by ALL consumer threads before K-chunk `ch` of the FIRST group is touched: a phase can then stage its
+// input chunk by chunk as the CTAs that produce it finish (pass a no-op when the input was staged up front).
+template <class Ready, class Pre, class Epi>
 __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages, RingState& rs,
-                                               const uint4* xs, int tid, Pre pre, Epi epi) {
+                                               const uint4* xs, int tid, Ready ready, Pre pre, Epi epi) {
   const MatCut c = cut_matrix(N, K);
   const int lane = tid & 31, warp = tid >> 5;
   const int kc8 = c.kc >> 3;  // 16-byte chunks per row chunk
   for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
     const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
-    if (warp < g) {
-      float a0 = 0.f, a1 = 0.f;
-      uint2 prefetched = make_uint2(0u, 0u);
-      if (lane == 0) prefetched = pre(2 * (g0 + warp));
-      for (int ch = 0; ch < c.nch; ++ch) {
+    float a0 = 0.f, a1 = 0.f;
+    uint2 prefetched = make_uint2(0u, 0u);
+    if (warp < g && lane == 0) prefetched = pre(2 * (g0 + warp));
+    for (int ch = 0; ch < c.nch; ++ch) {
+      if (g0 == c.p0) ready(ch);
+      if (warp < g) {
         const uint32_t it = rs.it + (uint32_t)(ch * g + warp);
         const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
         // Guard (tests/test_megakernel_protocol.py): bulk copies land out of order, so this warp may get here before the
@@ -404,6 +421,8 @@ __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring
         __syncwarp();
         if (lane == 0) mbar_arrive_n(&empty[slot], MK_CONSUMER_WARPS);  // this warp is the only reader of the slot
       }
+    }
+    if (warp < g) {
       a0 = warp_sum(a0);
       a1 = warp_sum(a1);
       if (lane == 0) epi(2 * (g0 + warp), a0, a1, prefetched);
@@ -719,7 +738,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       const float* rope_row = p.rope + (int64_t)p.pos * (kHeadDim / 2) * 2;
       bf16* ck = L.cache_k + (int64_t)slot_row * kv_dim;
       bf16* cv = L.cache_v + (int64_t)slot_row * kv_dim;
-      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid,
+      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {},
                      [&](int n) { return *reinterpret_cast<const uint2*>(rope_row + ((n & (kHeadDim - 1)) >> 1) * 2); },
                      [&](int n, float a0, float a1, uint2 pf) {
         const float y0 = round_bf16(a0), y1 = round_bf16(a1);
@@ -756,7 +775,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
     // ---- phase 3: wo + residual ----
     stage_x(xs, p.abuf, nullptr, q_dim, 0.f, red, tid);
-    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n) { return make_uint2(ldcg_u32(x_in + n), 0u); }, [&](int n, float a0, float a1, uint2 pf) {
+    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(x_in + n), 0u); }, [&](int n, float a0, float a1, uint2 pf) {
       const uint32_t r = pf.x;
       *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
     });
@@ -766,7 +785,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
     // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
     stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-    consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
+    consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
       const float s = round_bf16(ref_silu(round_bf16(a0)));
       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
     });
@@ -775,11 +794,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     mk_stamp(p, tid, l, 9);
 
     // ---- phase 5: down + residual ----
+    // (Tried: no full barrier here -- stage g chunk by chunk as the barrier words of the CTA range that produced each K-chunk
+    //  complete, via grid_arrive / grid_wait + the `ready` hook.  Correct, but 4 polling rounds + 4 block syncs cost more than
+    //  the ~5 us gate/up arrival skew they hide: 345 vs 351 tok/s.)
     stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
-    consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); }, [&](int n, float a0, float a1, uint2 pf) {
-      const uint32_t r = pf.x;
-      *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
-    });
+    consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
+                   [&](int n, float a0, float a1, uint2 pf) {
+                     const uint32_t r = pf.x;
+                     *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
+                   });
     mk_stamp(p, tid, l, 10);
     grid_barrier(p, tid, epoch, l, 5);
     mk_stamp(p, tid, l, 11);
@@ -787,7 +810,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
   // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) ----
   stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
-  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
+  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
     *reinterpret_cast<float2*>(p.logits + n) = make_float2(round_bf16(a0), round_bf16(a1));
   });
 }
