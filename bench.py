@@ -175,6 +175,7 @@ def run_ours(a, rank: int, world: int):
     del logits
 
     # ---- decode: device-resident loop (value) ----
+    fused_argmax = model._megakernel_ok(a.batch)  # greedy argmax is part of the decode kernel: the loop is one launch per token
     kern_ev = []  # (start, end) CUDA events around the hot-path launch of each timed step (the decode megakernel)
 
     def step(t, timed=False):
@@ -184,8 +185,9 @@ def run_ours(a, rank: int, world: int):
             lg = model.decode_static(t, cache)
             a1.record()
             kern_ev.append((a0, a1))
-            return lg.argmax(-1)
-        return model.decode_static(t, cache).argmax(-1)
+            return model.last_argmax if fused_argmax else lg.argmax(-1)
+        lg = model.decode_static(t, cache)
+        return model.last_argmax if fused_argmax else lg.argmax(-1)
 
     for _ in range(max(a.warmup, 3)):
         tok = step(tok)

@@ -144,6 +144,8 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
  *   token_dev    device int64 scalar (e.g. the previous step's argmax); pos = its absolute position;
  *                batch_row = which row of the [max_batch, W, KV, hd] cache this sequence occupies
  *   logits       [vocab] fp32
+ *   next_token_dev  optional device int64: greedy argmax of the logits, first index on ties (torch.argmax, generate.py:156);
+ *                NULL to skip.  Feeding it back as token_dev makes the greedy loop one launch per token, nothing on the host.
  * Requires a device that can co-schedule one CTA per SM (cooperative launch).
  */
 typedef struct mb200_layer_desc {
@@ -159,7 +161,7 @@ typedef struct mb200_layer_desc {
 
 int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb,
                       const void* final_norm, const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos,
-                      int64_t batch_row, float* logits, int64_t dim, int64_t hidden, int64_t n_heads, int64_t n_kv_heads,
+                      int64_t batch_row, float* logits, int64_t* next_token_dev, int64_t dim, int64_t hidden, int64_t n_heads, int64_t n_kv_heads,
                       int64_t head_dim, int64_t vocab, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
 #define MB200_SKINNY_MAX_T 4

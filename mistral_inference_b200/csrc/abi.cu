@@ -234,7 +234,8 @@ int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* l
 }
 
 int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb, const void* final_norm,
-                      const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos, int64_t batch_row, float* logits, int64_t dim,
+                      const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos, int64_t batch_row, float* logits,
+                      int64_t* next_token_dev, int64_t dim,
                       int64_t hidden, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int64_t vocab, float eps, void* workspace,
                       size_t workspace_bytes, void* stream) {
   static_assert(sizeof(mb200_layer_desc) == sizeof(MkLayer), "layer descriptor layout");
@@ -266,6 +267,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.pos = (int)pos;
   p.batch_row = (int)batch_row;
   p.logits = logits;
+  p.next_token = (long long*)next_token_dev;
   p.dim = (int)dim;
   p.hidden = (int)hidden;
   p.H = (int)n_heads;
@@ -291,6 +293,12 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
       cap = e ? atoi(e) : 5;  // B200 sweep (7B): 3 -> 3.02 ms/token, 4 -> 2.87, 6 -> 2.87, 8 -> 2.89, uncapped -> 2.92
     }
     p.inflight_cap = cap < 2 ? 2 : (cap > 8 ? 8 : cap);
+    static int kvu = -1;
+    if (kvu < 0) {
+      const char* e2 = getenv("MB200_MK_KV_UNCAPPED");
+      kvu = e2 ? atoi(e2) : 0;
+    }
+    p.kv_uncapped = kvu;
   }
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
 
@@ -299,6 +307,8 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   // global scratch: header words + activations + per-slice attention partials
   uint8_t* ws = (uint8_t*)workspace;
   p.attn_counters = (int*)(ws + 8192);
+  p.argmax_counter = (int*)(ws + 12288);
+  p.argmax_slots = (unsigned long long*)(ws + 32768);  // sms x 8 B
   p.bar_flags = (unsigned*)(ws + 16384);
   {
     // the barrier counter lives in the caller's workspace; its value is tracked per workspace on the host (stream-ordered launches)

@@ -32,7 +32,10 @@ namespace mb200 {
 
 constexpr int MK_CONSUMER_WARPS = 8;
 constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
-constexpr int MK_PRODUCER_WARPS = 2;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
+#ifndef MB200_MK_PRODUCERS
+#define MB200_MK_PRODUCERS 2
+#endif
+constexpr int MK_PRODUCER_WARPS = MB200_MK_PRODUCERS;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
 constexpr int MK_THREADS = MK_CONSUMERS + 32 * MK_PRODUCER_WARPS;
 constexpr int MK_WEIGHT_STAGE_BYTES = 16 * 1024;   // a weight stage: 2 rows x KC elements x 2 B
 constexpr int MK_MAX_KC = MK_WEIGHT_STAGE_BYTES / 4;  // elements per row chunk
@@ -64,10 +67,14 @@ struct MkParams {
   int pos;                 // absolute position of that token
   int batch_row;           // which row of the cache this sequence uses
   float* logits;           // [V] fp32
+  long long* next_token;   // optional: greedy argmax of the logits (first index on ties, like torch.argmax), or null
+  unsigned long long* argmax_slots;  // [gridDim] per-CTA (value, index) keys
+  int* argmax_counter;     // self-resetting
   int dim, hidden, H, KV, vocab;
   float eps;
   int n_stages, xs_bytes;
   int inflight_cap;  // max ring stages with outstanding bulk copies (< n_stages)
+  int kv_uncapped;
   // scratch (global)
   unsigned* bar_flags;  // grid barrier counter (monotonic, never reset)
   unsigned bar_base;    // number of barriers completed before this launch (host-tracked)
@@ -272,6 +279,7 @@ struct Producer {
   // phase vs 1.5 us in steady state).  The bandwidth-delay product of one SM's HBM share is only ~3 stages.
   int cap;
   int me, n_prod;          // this producer issues the stages with it % n_prod == me
+  bool kv_uncapped;        // K/V slice stages ignore the in-flight cap (they are needed at once in phase 2a)
   uint32_t slot, par;      // ring slot / parity of stage `it`, kept incrementally (no division in the issue loop)
   uint32_t cslot, cpar;    // same for stage it - cap
 
@@ -287,12 +295,12 @@ struct Producer {
     }
   }
   // returns the slot's buffer (and its full barrier, armed for `bytes`) or nullptr when the stage belongs to another producer
-  __device__ __forceinline__ uint8_t* acquire(uint32_t bytes, uint64_t*& bar) {
+  __device__ __forceinline__ uint8_t* acquire(uint32_t bytes, uint64_t*& bar, bool capped = true) {
     if ((int)(it % (uint32_t)n_prod) != me) {
       advance();
       return nullptr;
     }
-    if (it >= (uint32_t)cap) mbar_wait(&full[cslot], cpar, 7, it);  // stage it - cap has landed (its slot cannot have been refilled yet)
+    if (capped && it >= (uint32_t)cap) mbar_wait(&full[cslot], cpar, 7, it);  // stage it - cap has landed (its slot cannot have been refilled yet)
     mbar_wait(&empty[slot], par ^ 1, 1, it);
     bar = &full[slot];
     mbar_arrive_expect_tx(bar, bytes);
@@ -338,7 +346,7 @@ struct Producer {
 #pragma unroll
       for (int kv = 0; kv < 2; ++kv) {
         uint64_t* bar;
-        uint8_t* dst = acquire((uint32_t)rows * row_bytes, bar);
+        uint8_t* dst = acquire((uint32_t)rows * row_bytes, bar, !kv_uncapped);
         if (dst == nullptr) continue;
         const bf16* src = (kv ? vbase : kbase) + (int64_t)k0 * row_elems;
         for (int r = 0; r < rows; ++r) bulk_g2s_hint(dst + r * (row_bytes + MK_KV_PAD), src + (int64_t)r * row_elems, row_bytes, bar, policy);
@@ -357,6 +365,7 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
   pr.cap = p.inflight_cap;
   pr.me = me;
   pr.n_prod = MK_PRODUCER_WARPS;
+  pr.kv_uncapped = p.kv_uncapped != 0;
   pr.slot = pr.par = pr.cslot = pr.cpar = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.policy));
   const int q_dim = p.H * kHeadDim, kv_dim = p.KV * kHeadDim;
@@ -808,11 +817,45 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     mk_stamp(p, tid, l, 11);
   }
 
-  // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) ----
+  // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) + greedy argmax ----
   stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
-  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
-    *reinterpret_cast<float2*>(p.logits + n) = make_float2(round_bf16(a0), round_bf16(a1));
-  });
+  // argmax key: order-preserving map of the fp32 logit in the high word, ~index in the low word, so that the maximum key is
+  // the largest logit and, among equal logits, the SMALLEST index (what torch.argmax returns; generate.py:156)
+  unsigned long long best = 0ull;
+  auto key_of = [](float v, int idx) {
+    unsigned u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned)(0x7fffffff - idx);
+  };
+  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); },
+                 [&](int n, float a0, float a1, uint2) {
+                   const float y0 = round_bf16(a0), y1 = round_bf16(a1);
+                   *reinterpret_cast<float2*>(p.logits + n) = make_float2(y0, y1);
+                   const unsigned long long k0 = key_of(y0, n), k1 = key_of(y1, n + 1);
+                   best = max(best, max(k0, k1));
+                 });
+  if (p.next_token != nullptr) {
+    // lane 0 of every warp holds its pairs' best; CTA reduce through shared memory, then the last CTA to arrive reduces all
+    unsigned long long* sm_best = reinterpret_cast<unsigned long long*>(xs);
+    consumer_sync();
+    if ((tid & 31) == 0) sm_best[tid >> 5] = best;
+    consumer_sync();
+    if (tid == 0) {
+      unsigned long long b = 0ull;
+#pragma unroll
+      for (int w = 0; w < MK_CONSUMER_WARPS; ++w) b = max(b, sm_best[w]);
+      p.argmax_slots[blockIdx.x] = b;
+      __threadfence();
+      const int prev = atomicAdd(p.argmax_counter, 1);
+      if (prev == (int)gridDim.x - 1) {
+        *p.argmax_counter = 0;
+        __threadfence();
+        unsigned long long g = 0ull;
+        for (int c = 0; c < (int)gridDim.x; ++c) g = max(g, __ldcg(p.argmax_slots + c));
+        *p.next_token = (long long)(0x7fffffff - (int)(g & 0xffffffffull));
+      }
+    }
+  }
 }
 
 }  // namespace mb200

@@ -232,15 +232,22 @@ class Transformer(nn.Module):
                   "layers": torch.from_numpy(desc.view(np.int64)).to(self.device),
                   "windows": torch.tensor(cache.cache_sizes, dtype=torch.int32, device=self.device),
                   "token": torch.zeros(1, dtype=torch.long, device=self.device),
+                  "next": torch.zeros(1, dtype=torch.long, device=self.device),
                   "logits": torch.empty(1, self.vocab_size, dtype=torch.float32, device=self.device)}
             self._decode_graphs[key] = st
         if cache._kv_seqlens_host is None:
             cache.init_kvseqlens(1)
         pos = cache._kv_seqlens_host[0]
         assert pos < self.rope_table.shape[0]
-        st["token"].copy_(tokens.reshape(1), non_blocking=True)
+        # `tokens` may be the previous step's fused argmax (st["next"]): then nothing is copied and the greedy loop is one
+        # kernel launch per token
+        tok = tokens.reshape(1)
+        if tok.data_ptr() != st["next"].data_ptr():
+            st["token"].copy_(tok, non_blocking=True)
+            tok = st["token"]
+        self.last_argmax = st["next"]
         _abi.decode_step(st["layers"], st["windows"], self.n_local_layers, self.tok_embeddings.weight, self.norm.weight, self.output_weight,
-                         self.rope_table, st["token"], pos, 0, st["logits"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
+                         self.rope_table, tok, pos, 0, st["logits"], st["next"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
                          self.vocab_size, a.norm_eps, ws)
         cache.update_seqlens([1])
         return st["logits"]

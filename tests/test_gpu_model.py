@@ -186,6 +186,8 @@ def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
         return torch.cat(out[1:], 0), cache
 
     mk, c1 = run(True)
+    # fused greedy argmax of the last step == torch.argmax of the logits it produced (first index on ties)
+    assert int(m.last_argmax.item()) == int(mk[-1].argmax().item())
     per_op, c2 = run(False)
     d = report(f"megakernel vs per-op {shape}{over}", mk, per_op)
     assert d.max() <= LOGIT_ATOL
