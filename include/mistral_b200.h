@@ -146,6 +146,9 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
  *   logits       [vocab] fp32
  *   next_token_dev  optional device int64: greedy argmax of the logits, first index on ties (torch.argmax, generate.py:156);
  *                NULL to skip.  Feeding it back as token_dev makes the greedy loop one launch per token, nothing on the host.
+ *   n_experts/top_k  0/0 for dense FeedForward layers.  Mixture of experts (moe.py:16-32): the layer descriptors' w13/w2 are
+ *                ignored; moe_gate_dev [n_layers] (router weight [E, dim]), moe_w13_dev / moe_w2_dev [n_layers * E] are DEVICE arrays
+ *                of device pointers.  Router, top-k, softmax over the k and the ascending-expert bf16 accumulation run in-kernel.
  * Requires a device that can co-schedule one CTA per SM (cooperative launch).
  */
 typedef struct mb200_layer_desc {
@@ -162,7 +165,8 @@ typedef struct mb200_layer_desc {
 int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb,
                       const void* final_norm, const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos,
                       int64_t batch_row, float* logits, int64_t* next_token_dev, int64_t dim, int64_t hidden, int64_t n_heads, int64_t n_kv_heads,
-                      int64_t head_dim, int64_t vocab, float eps, void* workspace, size_t workspace_bytes, void* stream);
+                      int64_t head_dim, int64_t vocab, float eps, int64_t n_experts, int64_t top_k, const void* const* moe_gate_dev,
+                      const void* const* moe_w13_dev, const void* const* moe_w2_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 #define MB200_SKINNY_MAX_T 4
 

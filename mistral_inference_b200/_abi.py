@@ -39,7 +39,8 @@ _SIGNATURES = {
                               c_void_p]),
     "mb200_workspace_bytes": (c_size_t, [c_int64] * 8),
     "mb200_decode_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                  c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mb200_debug_set_decode_timeline": (c_int, [c_void_p]),
     "mb200_debug_set_barrier_timeline": (c_int, [c_void_p]),
     "mb200_test_gemm_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
@@ -173,10 +174,12 @@ def lm_head(x, norm_w, w_out, logits, eps, ws: Workspace) -> None:
 
 
 def decode_step(layers_dev, windows_dev, n_layers, emb, final_norm, w_out, rope, token_dev, pos, batch_row, logits, next_token, dim, hidden,
-                n_heads, n_kv_heads, head_dim, vocab, eps, ws: Workspace) -> None:
+                n_heads, n_kv_heads, head_dim, vocab, eps, ws: Workspace, n_experts: int = 0, top_k: int = 0, moe_gate=None, moe_w13=None,
+                moe_w2=None) -> None:
     _check(lib().mb200_decode_step(_ptr(layers_dev), _ptr(windows_dev), n_layers, _ptr(emb), _ptr(final_norm), _ptr(w_out), _ptr(rope),
-                                   _ptr(token_dev), pos, batch_row, _ptr(logits), _ptr(next_token), dim, hidden, n_heads, n_kv_heads, head_dim, vocab, eps,
-                                   ws.ptr, ws.nbytes, _stream()), "mb200_decode_step")
+                                   _ptr(token_dev), pos, batch_row, _ptr(logits), _ptr(next_token), dim, hidden, n_heads, n_kv_heads, head_dim,
+                                   vocab, eps, n_experts, top_k, _ptr(moe_gate), _ptr(moe_w13), _ptr(moe_w2), ws.ptr, ws.nbytes, _stream()),
+           "mb200_decode_step")
 
 
 def set_decode_timeline(buf: Optional[torch.Tensor]) -> None:

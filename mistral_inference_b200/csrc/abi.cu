@@ -86,7 +86,7 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
   s += align256((size_t)T * widest * 2);                                  // normed activations
   s += attn_decode_workspace(max_batch, n_kv_heads, 64, rep);             // split-KV partials (n_splits <= 64)
   // decode_step scratch (residual ping-pong, h, q, attn, g) lives in the same region as the normed activations
-  const size_t mk = 6 * 256 + (size_t)(3 * dim + 2 * n_heads * head_dim + hidden) * 2 +
+  const size_t mk = 6 * 256 + (size_t)(3 * dim + 2 * n_heads * head_dim + MK_MAX_TOPK * hidden) * 2 +
                     (size_t)256 * n_heads * (kHeadDim + 2) * sizeof(float) + 256;  // up to 256 SMs worth of attention slices
   if (s < kWsHeader + mk) s = kWsHeader + mk;
   return s;
@@ -236,8 +236,9 @@ int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* l
 int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb, const void* final_norm,
                       const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos, int64_t batch_row, float* logits,
                       int64_t* next_token_dev, int64_t dim,
-                      int64_t hidden, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int64_t vocab, float eps, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      int64_t hidden, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim, int64_t vocab, float eps, int64_t n_experts,
+                      int64_t top_k, const void* const* moe_gate_dev, const void* const* moe_w13_dev, const void* const* moe_w2_dev,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   static_assert(sizeof(mb200_layer_desc) == sizeof(MkLayer), "layer descriptor layout");
   MB_CHECK_ARG(layers_dev && windows_dev && emb && final_norm && w_out && rope && token_dev && logits && workspace, "decode_step: null pointer");
   MB_CHECK_ARG(head_dim == kHeadDim, "decode_step: head_dim=%lld unsupported (128 only)", (long long)head_dim);
@@ -268,6 +269,13 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.batch_row = (int)batch_row;
   p.logits = logits;
   p.next_token = (long long*)next_token_dev;
+  MB_CHECK_ARG(n_experts == 0 || (moe_gate_dev && moe_w13_dev && moe_w2_dev && top_k >= 1 && top_k <= MK_MAX_TOPK && top_k <= n_experts && n_experts <= 32),
+               "decode_step: bad MoE arguments (E=%lld, k=%lld)", (long long)n_experts, (long long)top_k);
+  p.n_experts = (int)n_experts;
+  p.top_k = (int)(n_experts ? top_k : 0);
+  p.moe_gate = (const bf16* const*)moe_gate_dev;
+  p.moe_w13 = (const bf16* const*)moe_w13_dev;
+  p.moe_w2 = (const bf16* const*)moe_w2_dev;
   p.dim = (int)dim;
   p.hidden = (int)hidden;
   p.H = (int)n_heads;
@@ -278,9 +286,10 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   int64_t widest = dim > hidden ? dim : hidden;
   if (q_dim > widest) widest = q_dim;
   size_t xs_bytes = (size_t)widest * 2;
+  if (n_experts && xs_bytes < (size_t)top_k * hidden * 2) xs_bytes = (size_t)top_k * hidden * 2;  // g of every selected expert
   if (xs_bytes < 2048) xs_bytes = 2048;  // also the slice-merge scratch of phase 2b
   xs_bytes = (xs_bytes + 127) & ~(size_t)127;
-  const size_t tail = 2 * MK_MAX_STAGES * sizeof(uint64_t) + (8 + 32 + 4) * sizeof(float) + 64;
+  const size_t tail = 2 * MK_MAX_STAGES * sizeof(uint64_t) + 48 * sizeof(float) + sizeof(MoeRoute) + 8 + 64;
   int n_stages = (int)(((size_t)smem_max - xs_bytes - tail) / MK_STAGE_BYTES);
   if (n_stages > MK_MAX_STAGES) n_stages = MK_MAX_STAGES;
   MB_CHECK_ARG(n_stages > MK_CONSUMER_WARPS, "decode_step: not enough shared memory for the weight ring (%d stages)", n_stages);
@@ -326,7 +335,7 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.hbuf = (bf16*)take((size_t)dim * 2);
   p.qbuf = (bf16*)take((size_t)q_dim * 2);
   p.abuf = (bf16*)take((size_t)q_dim * 2);
-  p.gbuf = (bf16*)take((size_t)hidden * 2);
+  p.gbuf = (bf16*)take((size_t)(n_experts ? top_k : 1) * hidden * 2);
   p.partial = (float*)take((size_t)sms * n_heads * (kHeadDim + 2) * sizeof(float));  // [slice = CTA][H][m, l, acc[128]]
   p.prof = g_mk_prof;
   p.prof_bar = g_mk_prof_bar;

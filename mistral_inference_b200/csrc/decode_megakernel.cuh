@@ -58,6 +58,11 @@ struct MkLayer {  // 64 bytes, device array prepared by the caller (include/mist
 struct MkParams {
   const MkLayer* layers;
   const int32_t* windows;  // [n_layers] ring size per layer
+  // Mixture of experts (moe.py:16-32): n_experts == 0 -> dense FeedForward (layers[l].w13 / w2)
+  int n_experts, top_k;
+  const bf16* const* moe_gate;  // [n_layers]              router weight [E, dim]
+  const bf16* const* moe_w13;   // [n_layers * n_experts]  expert gate/up, packed like w13
+  const bf16* const* moe_w2;    // [n_layers * n_experts]  expert down
   int n_layers;
   const bf16* emb;         // [V, dim]
   const bf16* final_norm;  // [dim]
@@ -223,6 +228,13 @@ __device__ __forceinline__ MatCut cut_matrix(int N, int K) {
   return c;
 }
 
+// routing decision of one MoE layer (moe.py:24-32), produced on every CTA by moe_route
+constexpr int MK_MAX_TOPK = 4;
+struct MoeRoute {
+  int e[MK_MAX_TOPK];    // selected experts in ASCENDING expert index (the order `results +=` runs in, moe.py:29-31)
+  float w[MK_MAX_TOPK];  // their routing weights (bf16 values)
+};
+
 struct RingState {
   uint32_t it;  // running stage counter (same sequence in producer and consumers)
 };
@@ -332,6 +344,32 @@ struct Producer {
     }
   }
 
+  // expert down projections of one MoE layer: per group of 8 pairs expert-major, chunk-major (see consume_moe_down)
+  __device__ __forceinline__ void moe_down(const bf16* const* w2, const int* sel, int top_k, int N, int K) {
+    const MatCut c = cut_matrix(N, K);
+    const uint32_t row_bytes = (uint32_t)c.kc * 2;
+    for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
+      const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
+      for (int j = 0; j < top_k; ++j) {
+        const bf16* W = w2[sel[j]];
+        for (int ch = 0; ch < c.nch; ++ch) {
+          for (int w = 0; w < g; ++w) {
+            const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
+            uint64_t* bar;
+            uint8_t* dst = acquire(2 * row_bytes, bar);
+            if (dst == nullptr) continue;
+            if (c.nch == 1) {
+              bulk_g2s_hint(dst, r0, 2 * row_bytes, bar, policy);
+            } else {
+              bulk_g2s_hint(dst, r0 + ch * c.kc, row_bytes, bar, policy);
+              bulk_g2s_hint(dst + row_bytes, r0 + K + ch * c.kc, row_bytes, bar, policy);
+            }
+          }
+        }
+      }
+    }
+  }
+
   // this CTA's K and V slice: alternating K / V stages of `pps` positions; one copy per position row so that rows sit
   // (row_bytes + 16) apart in shared memory (8 consecutive rows then cover all 32 banks for ldmatrix)
   __device__ __forceinline__ void kv_slice(const MkParams& p, const MkLayer& L, int W) {
@@ -355,7 +393,8 @@ struct Producer {
   }
 };
 
-__device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int me) {
+__device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int me, const MoeRoute* route,
+                                              uint64_t* route_bar) {
   Producer pr;
   pr.ring = ring;
   pr.full = full;
@@ -374,8 +413,18 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
     pr.matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim);
     pr.kv_slice(p, L, p.windows[l]);
     pr.matrix(L.wo, p.dim, q_dim);
-    pr.matrix(L.w13, 2 * p.hidden, p.dim);
-    pr.matrix(L.w2, p.dim, p.hidden);
+    if (p.n_experts == 0) {
+      pr.matrix(L.w13, 2 * p.hidden, p.dim);
+      pr.matrix(L.w2, p.dim, p.hidden);
+    } else {
+      // expert weights are data dependent: wait for this layer's routing decision (the only point where the weight stream
+      // cannot run ahead of the activations)
+      mbar_wait(route_bar, (uint32_t)(l & 1), 8, (uint32_t)l);
+      int sel[MK_MAX_TOPK];
+      for (int j = 0; j < p.top_k; ++j) sel[j] = route->e[j];
+      for (int j = 0; j < p.top_k; ++j) pr.matrix(p.moe_w13[l * p.n_experts + sel[j]], 2 * p.hidden, p.dim);
+      pr.moe_down(p.moe_w2 + l * p.n_experts, sel, p.top_k, p.dim, p.hidden);
+    }
   }
   pr.matrix(p.w_out, p.vocab, p.dim);
 }
@@ -699,6 +748,122 @@ __device__ __forceinline__ void mk_attention_combine(const MkParams& p, int W, i
   }
 }
 
+// ---- mixture of experts (moe.py:24-32), batch 1 ------------------------------------------------------------------------------
+
+// Router on every CTA (identical, deterministic): logits = bf16(hn . gate^T) (one warp per expert), top-k on the bf16 logits,
+// softmax over the k selected in fp32, rounded to bf16 (moe.py:25-27).  Ties: lower expert index first.
+__device__ __forceinline__ void moe_route(const MkParams& p, int layer, const uint4* xs, float* red, MoeRoute* route, uint64_t* route_bar, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const bf16* gate = p.moe_gate[layer];
+  const int kc = p.dim >> 3;
+  for (int e = warp; e < p.n_experts; e += MK_CONSUMER_WARPS) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(gate + (int64_t)e * p.dim);
+    float acc = 0.f;
+    for (int i = lane; i < kc; i += 32) {
+      const uint4 a = __ldg(wrow + i), x = xs[i];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc = fmaf(bf16lo(aw[j]), bf16lo(xw[j]), acc);
+        acc = fmaf(bf16hi(aw[j]), bf16hi(xw[j]), acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[8 + e] = round_bf16(acc);  // red[8..8+E): router logits (E <= 32)
+  }
+  consumer_sync();
+  if (tid == 0) {
+    int sel[MK_MAX_TOPK];
+    float val[MK_MAX_TOPK];
+    unsigned taken = 0;
+    for (int j = 0; j < p.top_k; ++j) {
+      int best = -1;
+      for (int e = 0; e < p.n_experts; ++e)
+        if (!((taken >> e) & 1u) && (best < 0 || red[8 + e] > red[8 + best])) best = e;
+      taken |= 1u << best;
+      sel[j] = best;
+      val[j] = red[8 + best];
+    }
+    float den = 0.f, ex[MK_MAX_TOPK];
+    for (int j = 0; j < p.top_k; ++j) {
+      ex[j] = expf(val[j] - val[0]);  // val[0] is the maximum
+      den += ex[j];
+    }
+    for (int j = 0; j < p.top_k; ++j) val[j] = round_bf16(ex[j] / den);
+    // ascending expert order, weights travelling with their experts
+    for (int a = 1; a < p.top_k; ++a)
+      for (int b = a; b > 0 && sel[b] < sel[b - 1]; --b) {
+        const int ts = sel[b];
+        sel[b] = sel[b - 1];
+        sel[b - 1] = ts;
+        const float tv = val[b];
+        val[b] = val[b - 1];
+        val[b - 1] = tv;
+      }
+    for (int j = 0; j < p.top_k; ++j) {
+      route->e[j] = sel[j];
+      route->w[j] = val[j];
+    }
+    mbar_arrive(route_bar);  // release: the producers may read `route` and start streaming the selected experts
+  }
+  consumer_sync();
+}
+
+// Expert down projections with the reference's accumulation: for the selected experts in ascending index,
+//   y_e = bf16(W2_e g_e);  t_e = bf16(w_e * y_e);  res = (first ? t_e : bf16(res + t_e));   out = bf16(h + res)
+// Stage order per group of 8 pairs: expert-major, then chunk-major (mirrored by Producer::moe_down).
+template <class Pre, class Epi>
+__device__ __forceinline__ void consume_moe_down(const MkParams& p, const MoeRoute& rt, const uint8_t* ring, uint64_t* full, uint64_t* empty,
+                                                 int n_stages, RingState& rs, const uint4* xs, int tid, Pre pre, Epi epi) {
+  const MatCut c = cut_matrix(p.dim, p.hidden);
+  const int lane = tid & 31, warp = tid >> 5;
+  const int kc8 = c.kc >> 3;
+  const int hid8 = p.hidden >> 3;
+  for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
+    const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
+    if (warp < g) {
+      uint2 prefetched = make_uint2(0u, 0u);
+      if (lane == 0) prefetched = pre(2 * (g0 + warp));
+      float r0 = 0.f, r1 = 0.f;
+      for (int j = 0; j < p.top_k; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int ch = 0; ch < c.nch; ++ch) {
+          const uint32_t it = rs.it + (uint32_t)((j * c.nch + ch) * g + warp);
+          const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
+          mbar_wait(&empty[slot], par ^ 1, 2, it);
+          mbar_wait(&full[slot], par, 3, it);
+          const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
+          const uint4* w1 = w0 + kc8;
+          const uint4* xc = xs + j * hid8 + ch * kc8;
+#pragma unroll 4
+          for (int i = lane; i < kc8; i += 32) {
+            const uint4 a = w0[i], b = w1[i], x = xc[i];
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float xl = bf16lo(xw[q]), xh = bf16hi(xw[q]);
+              a0 = fmaf(bf16lo(aw[q]), xl, a0);
+              a0 = fmaf(bf16hi(aw[q]), xh, a0);
+              a1 = fmaf(bf16lo(bw[q]), xl, a1);
+              a1 = fmaf(bf16hi(bw[q]), xh, a1);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_n(&empty[slot], MK_CONSUMER_WARPS);
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        const float t0 = round_bf16(rt.w[j] * round_bf16(a0)), t1 = round_bf16(rt.w[j] * round_bf16(a1));
+        r0 = (j == 0) ? t0 : round_bf16(r0 + t0);  // results starts at zero: bf16(0 + t) == t
+        r1 = (j == 0) ? t1 : round_bf16(r1 + t1);
+      }
+      if (lane == 0) epi(2 * (g0 + warp), r0, r1, prefetched);
+    }
+    rs.it += (uint32_t)(g * c.nch * p.top_k);
+    consumer_sync();
+  }
+}
+
 template <int REP>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -708,6 +873,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + p.xs_bytes);
   uint64_t* empty = full + MK_MAX_STAGES;
   float* red = reinterpret_cast<float*>(empty + MK_MAX_STAGES);                       // [8]
+  MoeRoute* route = reinterpret_cast<MoeRoute*>(red + 48);                            // routing decision of the current MoE layer
+  uint64_t* route_bar = reinterpret_cast<uint64_t*>(route + 1);                       // consumers -> producers: "route is valid"
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -715,6 +882,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], MK_CONSUMER_WARPS);  // weight stages: the owning warp arrives x8; K/V stages: every warp x1
     }
+    mbar_init(route_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -725,7 +893,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
   if (tid >= MK_CONSUMERS) {
     // ================= producers (one thread per producer warp; weights and old K/V rows never wait for activations) =================
-    if ((tid & 31) == 0) producer_main(p, ring, full, empty, (tid - MK_CONSUMERS) >> 5);
+    if ((tid & 31) == 0) producer_main(p, ring, full, empty, (tid - MK_CONSUMERS) >> 5, route, route_bar);
     return;
   }
 
@@ -792,26 +960,50 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     grid_barrier(p, tid, epoch, l, 3);
     mk_stamp(p, tid, l, 7);
 
+    if (p.n_experts == 0) {
     // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
-    stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-    consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
-      const float s = round_bf16(ref_silu(round_bf16(a0)));
-      p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
-    });
-    mk_stamp(p, tid, l, 8);
-    grid_barrier(p, tid, epoch, l, 4);
-    mk_stamp(p, tid, l, 9);
+      stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
+      consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
+        const float s = round_bf16(ref_silu(round_bf16(a0)));
+        p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
+      });
+      mk_stamp(p, tid, l, 8);
+      grid_barrier(p, tid, epoch, l, 4);
+      mk_stamp(p, tid, l, 9);
 
-    // ---- phase 5: down + residual ----
-    // (Tried: no full barrier here -- stage g chunk by chunk as the barrier words of the CTA range that produced each K-chunk
-    //  complete, via grid_arrive / grid_wait + the `ready` hook.  Correct, but 4 polling rounds + 4 block syncs cost more than
-    //  the ~5 us gate/up arrival skew they hide: 345 vs 351 tok/s.)
-    stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
-    consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
-                   [&](int n, float a0, float a1, uint2 pf) {
-                     const uint32_t r = pf.x;
-                     *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
-                   });
+      // ---- phase 5: down + residual ----
+      // (Tried: no full barrier here -- stage g chunk by chunk as the barrier words of the CTA range that produced each K-chunk
+      //  complete, via grid_arrive / grid_wait + the `ready` hook.  Correct, but 4 polling rounds + 4 block syncs cost more than
+      //  the ~5 us gate/up arrival skew they hide: 345 vs 351 tok/s.)
+      stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
+      consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
+                     [&](int n, float a0, float a1, uint2 pf) {
+                       const uint32_t r = pf.x;
+                       *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
+                     });
+    } else {
+      // ---- phase 4 (MoE): RMSNorm + router; gate/up + SiLU*mul of the selected experts (ascending expert index) ----
+      stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
+      moe_route(p, l, xs, red, route, route_bar, tid);
+      const MoeRoute rt = *route;
+      for (int j = 0; j < p.top_k; ++j) {
+        bf16* gj = p.gbuf + (size_t)j * p.hidden;
+        consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); },
+                       [&](int n, float a0, float a1, uint2) {
+                         const float sv = round_bf16(ref_silu(round_bf16(a0)));
+                         gj[n >> 1] = __float2bfloat16_rn(sv * round_bf16(a1));
+                       });
+      }
+      mk_stamp(p, tid, l, 8);
+      grid_barrier(p, tid, epoch, l, 4);
+      mk_stamp(p, tid, l, 9);
+      // ---- phase 5 (MoE): expert down projections, weighted bf16 accumulation in expert order, + residual ----
+      stage_x(xs, p.gbuf, nullptr, p.top_k * p.hidden, 0.f, red, tid);
+      consume_moe_down(p, rt, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
+                       [&](int n, float r0, float r1, uint2 pf) {
+                         *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(r0 + bf16lo(pf.x), r1 + bf16hi(pf.x));
+                       });
+    }
     mk_stamp(p, tid, l, 10);
     grid_barrier(p, tid, epoch, l, 5);
     mk_stamp(p, tid, l, 11);

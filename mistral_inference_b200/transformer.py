@@ -202,15 +202,18 @@ class Transformer(nn.Module):
 
     # ------------------------------------------------------------------ CUDA-graph decode
     def _graph_decode_ok(self, seqlens: List[int], cache: Optional[BufferCache]) -> bool:
-        if cache is None or self.num_pipeline_ranks != 1 or self.args.moe is not None:
-            return False  # the round-1 MoE layer still has host-side routing syncs
+        if cache is None or self.num_pipeline_ranks != 1:
+            return False
+        if self.args.moe is not None and not self._megakernel_ok(len(seqlens)):
+            return False  # the per-op MoE layer has host-side routing syncs (not capturable); batch-1 decode runs in the megakernel
         if os.environ.get("MB200_DECODE_GRAPH", "1") == "0":
             return False
         host = cache._kv_seqlens_host
         return host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
 
     def _megakernel_ok(self, B: int) -> bool:
-        return B == 1 and self.args.moe is None and self.num_pipeline_ranks == 1 and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
+        return (B == 1 and self.num_pipeline_ranks == 1 and self.args.n_kv_heads <= 8 and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
+                and (self.args.moe is None or (self.args.moe.num_experts <= 32 and self.args.moe.num_experts_per_tok <= 4)))
 
     def _decode_megakernel(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
         """Batch-1 decode step as ONE persistent cooperative kernel (csrc/decode_megakernel.cuh)."""
@@ -223,12 +226,24 @@ class Transformer(nn.Module):
         if st is None or st["cache"] is not cache:
             blocks = list(self.layers.values())
             desc = np.zeros((len(blocks), 8), dtype=np.uint64)
+            moe = self.args.moe
+            E = moe.num_experts if moe is not None else 0
+            gate_tab, w13_tab, w2_tab = [], [], []
             for i, blk in enumerate(blocks):
                 ff = blk.feed_forward
-                desc[i] = [blk.attention.wqkv.data_ptr(), blk.attention.wo_weight.data_ptr(), ff.w13.data_ptr(), ff.w2_weight.data_ptr(),
+                if moe is None:
+                    w13p, w2p = ff.w13.data_ptr(), ff.w2_weight.data_ptr()
+                else:  # the kernel reads the expert tables instead
+                    w13p = w2p = 0
+                    gate_tab.append(ff.gate_weight.data_ptr())
+                    w13_tab += [ex.w13.data_ptr() for ex in ff.experts]
+                    w2_tab += [ex.w2_weight.data_ptr() for ex in ff.experts]
+                desc[i] = [blk.attention.wqkv.data_ptr(), blk.attention.wo_weight.data_ptr(), w13p, w2p,
                            blk.attention_norm.weight.data_ptr(), blk.ffn_norm.weight.data_ptr(), cache.cache_k[i].data_ptr(),
                            cache.cache_v[i].data_ptr()]
-            st = {"cache": cache,
+            tab = lambda v: torch.tensor(v, dtype=torch.int64, device=self.device) if v else None  # noqa: E731
+            st = {"cache": cache, "E": E, "k": moe.num_experts_per_tok if moe is not None else 0,
+                  "moe_gate": tab(gate_tab), "moe_w13": tab(w13_tab), "moe_w2": tab(w2_tab),
                   "layers": torch.from_numpy(desc.view(np.int64)).to(self.device),
                   "windows": torch.tensor(cache.cache_sizes, dtype=torch.int32, device=self.device),
                   "token": torch.zeros(1, dtype=torch.long, device=self.device),
@@ -248,7 +263,7 @@ class Transformer(nn.Module):
         self.last_argmax = st["next"]
         _abi.decode_step(st["layers"], st["windows"], self.n_local_layers, self.tok_embeddings.weight, self.norm.weight, self.output_weight,
                          self.rope_table, tok, pos, 0, st["logits"], st["next"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
-                         self.vocab_size, a.norm_eps, ws)
+                         self.vocab_size, a.norm_eps, ws, st["E"], st["k"], st["moe_gate"], st["moe_w13"], st["moe_w2"])
         cache.update_seqlens([1])
         return st["logits"]
 

@@ -29,7 +29,8 @@ def model_for(p, max_batch=1):
 
 for name, over, prompt_len, steps in [("tiny", {}, 9, 4), ("tiny", {"sliding_window": 6}, 9, 8),
                                       ("mistral-7b", {"n_layers": 2, "vocab_size": 4096, "sliding_window": 64}, 100, 4),
-                                      ("mistral-7b", {"n_layers": 8}, 0, 4)]:
+                                      ("mistral-7b", {"n_layers": 8}, 0, 4), ("tiny-moe", {}, 9, 4),
+                                      ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 0, 4)]:
     p = synth.shape(name, **over)
     log("==", name, over)
     m = model_for(p)

@@ -169,6 +169,9 @@ def test_full_size_7b_layer_properties():
     ("tiny", {"sliding_window": 6}, 9, 12),                 # ring wraps
     ("tiny", {"sliding_window": [5, None]}, 20, 8),
     ("mistral-7b", {"n_layers": 2, "vocab_size": 4096, "sliding_window": 64}, 100, 6),  # real layer shapes (K chunks of 3584)
+    ("tiny-moe", {}, 9, 10),                                  # in-kernel router + experts (moe.py:24-32)
+    ("tiny-moe", {"sliding_window": 5}, 12, 8),
+    ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 40, 4),  # real expert shapes: 2 x (8 experts x 176 M params)
 ])
 def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
     """The persistent one-kernel-per-token decode step against (a) the per-op kernel path and (b) the CPU oracle."""
@@ -189,17 +192,18 @@ def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
     # fused greedy argmax of the last step == torch.argmax of the logits it produced (first index on ties)
     assert int(m.last_argmax.item()) == int(mk[-1].argmax().item())
     per_op, c2 = run(False)
+    moe = p.get("moe") is not None
     d = report(f"megakernel vs per-op {shape}{over}", mk, per_op)
-    assert d.max() <= LOGIT_ATOL
-    for i in c1.cache_k:  # the rings written by both paths agree (1 bf16 ulp on a few elements)
+    check_logits(d, moe)
+    for i in ([] if moe else c1.cache_k):  # (an expert flip changes later layers' K/V legitimately: dense models only)  # the rings written by both paths agree (1 bf16 ulp on a few elements)
         a, b = c1.cache_k[i][0].float(), c2.cache_k[i][0].float()
         ok = torch.isfinite(b)
         assert torch.equal(torch.isfinite(a), ok)
         assert (a[ok] - b[ok]).abs().max() <= 0.07
-    if shape == "tiny":
+    if shape.startswith("tiny"):
         om = oracle_model(p, 1)
         oc = om.new_cache(prompt_len + steps + 1)
         om.forward(torch.tensor(prompt), [prompt_len], oc)
         want = torch.cat([om.forward(torch.tensor([t]), [1], oc) for t in toks], 0)
         d = report(f"megakernel vs oracle {shape}{over}", mk, want)
-        assert d.max() <= LOGIT_ATOL
+        check_logits(d, moe)
