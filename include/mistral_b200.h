@@ -97,6 +97,8 @@ int mb200_attn_decode(const void* q, const void* cache_k, const void* cache_v, c
  *   q [T, H*hd]; k_new, v_new [T, KV*hd]; cache_k/v [max_batch, W, KV, hd]; out [T, H*hd] (all bf16)
  *   q_start [B+1] int32 (prefix sums of seqlens), seqpos [B] int32 (tokens already cached) -- device arrays
  *   max_seqlen: max over b of seqlens[b] (grid sizing);  window = W (cache size of this layer)
+ *   causal = 2: like 1, and the caller guarantees seqpos[b] == 0 for every sequence (first prefill, cache.py:236-240): no key
+ *               comes from the ring, which lets large chunks run on the tcgen05 / TMEM / TMA kernel.
  *   causal = 0: the cache-less forward (transformer_layers.py:72-73,88 with mask=None): every query attends
  *               to every new key of the whole flattened batch; ring, q_start, seqpos are ignored.
  */

@@ -147,9 +147,9 @@ def attn_decode(q, cache_k, cache_v, kv_len, out, n_heads, n_kv_heads, head_dim,
 
 
 def attn_prefill(q, k_new, v_new, cache_k, cache_v, q_start, seqpos, out, B, max_seqlen, W, n_heads, n_kv_heads, head_dim,
-                 causal: bool) -> None:
+                 causal: bool, first_prefill: bool = False) -> None:
     _check(lib().mb200_attn_prefill(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(cache_k), _ptr(cache_v), _ptr(q_start), _ptr(seqpos),
-                                    _ptr(out), q.shape[0], B, max_seqlen, W, n_heads, n_kv_heads, head_dim, 1 if causal else 0,
+                                    _ptr(out), q.shape[0], B, max_seqlen, W, n_heads, n_kv_heads, head_dim, (2 if first_prefill else 1) if causal else 0,
                                     _stream()), "mb200_attn_prefill")
 
 

@@ -39,6 +39,7 @@ class CacheInputMetadata:
     q_start: torch.Tensor     # [B+1] prefix sums of seqlens
     seqpos: torch.Tensor      # [B] tokens already cached before this forward
     prefill: bool             # first or subsequent prefill (cache.py:236-237); False = one-token decode
+    first_prefill: bool       # nothing cached yet for any sequence (cache.py:236,239)
     seqlens: List[int]
     max_seqlen: int
     window: int               # W of this layer
@@ -151,7 +152,7 @@ class BufferCache:
         distinct = sorted(set(self.cache_sizes))
         total = T + (B + 1) + B + len(distinct) * (T + B)
         host = np.empty(total, dtype=np.int32)
-        layout = {"T": T, "B": B, "prefill": first_prefill or subsequent_prefill, "max_seqlen": int(sl.max()), "windows": distinct}
+        layout = {"T": T, "B": B, "prefill": first_prefill or subsequent_prefill, "first_prefill": first_prefill, "max_seqlen": int(sl.max()), "windows": distinct}
         o = 0
         host[o:o + T] = positions; o += T
         host[o:o + B + 1] = q_start; o += B + 1
@@ -174,5 +175,5 @@ class BufferCache:
             rows = dev[o:o + T]; o += T
             kv_len = dev[o:o + B]; o += B
             per_w[W] = CacheInputMetadata(positions=positions, cache_rows=rows, kv_len=kv_len, q_start=q_start, seqpos=seqpos,
-                                          prefill=layout["prefill"], seqlens=list(seqlens), max_seqlen=layout["max_seqlen"], window=W)
+                                          prefill=layout["prefill"], first_prefill=layout["first_prefill"], seqlens=list(seqlens), max_seqlen=layout["max_seqlen"], window=W)
         return [per_w[W] for W in self.cache_sizes]

@@ -3,6 +3,7 @@
 
 #include "attn_decode.cuh"
 #include "attn_prefill.cuh"
+#include "attn_prefill_tcgen05.cuh"
 #include "decode_megakernel.cuh"
 #include "elementwise.cuh"
 #include "gemm_mma.cuh"
@@ -180,6 +181,8 @@ int mb200_attn_prefill(const void* q, const void* k_new, const void* v_new, cons
   MB_CHECK_ARG(head_dim == kHeadDim, "attn_prefill: head_dim=%lld unsupported (128 only)", (long long)head_dim);
   MB_CHECK_ARG(n_heads % n_kv_heads == 0, "attn_prefill: H %% KV != 0");
   if (T == 0) return MB200_OK;
+  if (causal == 2 && tcgen05_attn_eligible(T, max_seqlen))  // first prefill: every key comes from the chunk -> tcgen05 / TMEM / TMA kernel
+    return launch_attn_prefill_tcgen05(q, k_new, v_new, q_start, out, T, B, max_seqlen, W, n_heads, n_kv_heads, (cudaStream_t)stream);
   AttnPrefillParams p;
   p.q = (const bf16*)q;
   p.k_new = (const bf16*)k_new;
@@ -319,16 +322,8 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
   p.argmax_counter = (int*)(ws + 12288);
   p.argmax_slots = (unsigned long long*)(ws + 32768);  // sms x 8 B
   p.bar_flags = (unsigned*)(ws + 16384);
-  {
-    // the barrier counter lives in the caller's workspace; its value is tracked per workspace on the host (stream-ordered launches)
-    static std::mutex mu;
-    static std::unordered_map<void*, unsigned> base;
-    std::lock_guard<std::mutex> lk(mu);
-    unsigned& b = base[(void*)ws];
-    p.bar_base = b;
-    b += (unsigned)(6 * n_layers);  // six grid barriers per layer
-  }
-  MB_CHECK_ARG((size_t)n_kv_heads * sizeof(int) <= 4096, "decode_step: too many kv heads");
+  p.bar_epoch = (unsigned*)(ws + 20480);
+  p.done_counter = (int*)(ws + 20480 + 128);
   size_t off = kWsHeader;
   auto take = [&](size_t bytes) { uint8_t* r = ws + off; off += align256(bytes); return r; };
   p.xbuf = (bf16*)take((size_t)2 * dim * 2);

@@ -82,7 +82,8 @@ struct MkParams {
   int kv_uncapped;
   // scratch (global)
   unsigned* bar_flags;  // grid barrier counter (monotonic, never reset)
-  unsigned bar_base;    // number of barriers completed before this launch (host-tracked)
+  unsigned* bar_epoch;  // device word: number of barriers completed by previous launches (published by the last CTA to finish)
+  int* done_counter;    // self-resetting: CTAs that have finished this launch
   int* attn_counters;   // [KV]
   bf16* xbuf;           // [2][dim] residual stream ping-pong
   bf16* hbuf;           // [dim]
@@ -168,6 +169,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // Arrivals are spread over MK_BAR_WORDS counters on different 128-byte lines (CTA c -> word c % 8): when all CTAs arrive
 // within ~0.5 us (after the short wo / down phases) 148 same-address atomics serialise at one L2 slice (~3 us measured).
 constexpr int MK_BAR_WORDS = 8;
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_add_release_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -898,7 +902,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   }
 
   // ================= consumer warps =================
-  unsigned epoch = p.bar_base;  // barriers completed so far
+  // barriers completed by previous launches on this workspace.  Nobody writes the word until every CTA of this launch has
+  // finished (see the end of the kernel), and launches are stream ordered, so this read cannot race.
+  unsigned epoch = ld_acquire_u32(p.bar_epoch);
+  const unsigned epoch0 = epoch;
   const int64_t token = *p.token;
   for (int l = 0; l < p.n_layers; ++l) {
     const MkLayer L = p.layers[l];
@@ -1048,6 +1055,17 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       }
     }
   }
+  // publish the barrier epoch for the next launch: the last CTA to get here (all CTAs are past every barrier by then)
+  consumer_sync();
+  if (tid == 0) {
+    __threadfence();
+    const int prev = atomicAdd(p.done_counter, 1);
+    if (prev == (int)gridDim.x - 1) {
+      *p.done_counter = 0;
+      st_release_u32(p.bar_epoch, epoch);
+    }
+  }
+  (void)epoch0;
 }
 
 }  // namespace mb200

@@ -93,7 +93,7 @@ class Attention(nn.Module):
             # read the old ring, THEN write (transformer_layers.py:75-76)
             _abi.attn_qkv(x, norm_w, self.wqkv, rope, positions, q, k, v, None, None, None, H, KV, hd, eps, ws)
             _abi.attn_prefill(q, k, v, cache.cache_k, cache.cache_v, md.q_start, md.seqpos, out, len(md.seqlens), md.max_seqlen,
-                              md.window, H, KV, hd, causal=True)
+                              md.window, H, KV, hd, causal=True, first_prefill=md.first_prefill)
             _abi.kv_ring_write(k, v, cache.cache_k, cache.cache_v, md.cache_rows, KV, hd)
         else:
             # write, THEN read the ring (transformer_layers.py:78-81); the scatter is the QKV kernel's epilogue

@@ -192,11 +192,13 @@ def _oracle_prefill(q, k_new, v_new, ck, cv, seqlens, seqpos, W, H, KV):
     ([65, 3], [100, 250], 128),              # chunk on top of a wrapped ring, ragged
     ([1, 9], [40, 3], 16),                   # a one-token sequence inside a prefill batch
     ([300], [0], 4096),
+    ([700, 260], [0, 0], 4096),              # tcgen05 kernel: several 128-key tiles, ragged
+    ([700, 260], [0, 0], 200),               # ... with a window smaller than the sequence
 ])
 @pytest.mark.parametrize("H,KV", [(4, 2), (32, 8)])
 def test_attn_prefill(seqlens, seqpos, W, H, KV):
-    if (H, KV) == (32, 8) and sum(seqlens) > 150:
-        pytest.skip("big head count: small cases only")
+    if (H, KV) == (32, 8) and sum(seqlens) > 150 and sum(seqlens) < 900:
+        pytest.skip("big head count: small and tcgen05-sized cases only")
     T, B = sum(seqlens), len(seqlens)
     q, k_new, v_new = rnd(T, H * 128, seed=23), rnd(T, KV * 128, seed=24), rnd(T, KV * 128, seed=25)
     ck, cv = torch.zeros(B, W, KV, 128, dtype=torch.bfloat16), torch.zeros(B, W, KV, 128, dtype=torch.bfloat16)
@@ -214,7 +216,7 @@ def test_attn_prefill(seqlens, seqpos, W, H, KV):
     q_start = torch.tensor([0] + torch.tensor(seqlens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
     out = torch.zeros(T, H * 128, dtype=torch.bfloat16, device=DEV)
     _abi.attn_prefill(q.to(DEV), k_new.to(DEV), v_new.to(DEV), ck_d, cv_d, q_start, torch.tensor(seqpos, dtype=torch.int32, device=DEV), out,
-                      B, max(seqlens), W, H, KV, 128, causal=True)
+                      B, max(seqlens), W, H, KV, 128, causal=True, first_prefill=all(x == 0 for x in seqpos))
     assert_bf16_close(out, want, max_ulp=2, min_exact=0.5, atol=4e-3, what="prefill attention")
 
 
