@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z, g = h / (p.H / p.KV);
+  const int h = blockIdx.x, b = blockIdx.z, g = h / (p.H / p.KV);
   const int tok0 = p.q_start[b], s_len = p.q_start[b + 1] - tok0;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavier (later) query tiles first
+  // Heads vary fastest and the heavier (later) query tiles are dispatched first: longest-processing-time order for the causal
+  // triangle, and the query heads of one KV group read the same K/V tiles at the same time (L2 locality).
+  const int qt = (int)gridDim.y - 1 - (int)blockIdx.y;
   const int i0 = qt * FA_BM;
   if (i0 >= s_len) return;
   const int i_end = min(i0 + FA_BM, s_len);
@@ -176,8 +178,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       uint32_t sv[4][32];
       float mraw = -3.0e38f;
 #pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32_nowait(scol + c * 32, sv[c]);
+      tmem_wait_ld();
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        tmem_ld_32x32b_x32(scol + c * 32, sv[c]);
         if (edge) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -304,7 +308,7 @@ inline int launch_attn_prefill_tcgen05(const void* q, const void* k_new, const v
   p.KV = (int)KV;
   p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
   MB_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-  const dim3 grid((unsigned)ceil_div(max_seqlen, FA_BM), (unsigned)H, (unsigned)B);
+  const dim3 grid((unsigned)H, (unsigned)ceil_div(max_seqlen, FA_BM), (unsigned)B);
   attn_prefill_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   MB_CHECK_LAUNCH("attn_prefill_tcgen05_kernel");
   return MB200_OK;

@@ -77,4 +77,97 @@ __device__ __forceinline__ void epi_pair(const EpiParams& p, int t, int n, float
   }
 }
 
+// ---- row-chunk epilogues for the tcgen05 GEMM -------------------------------------------------------------------------------
+// There one thread owns one output row and reads its accumulator out of TMEM 32 columns at a time, so the natural unit is
+// (row t, columns n .. n+31) with n a multiple of 32: the chunk never straddles a head or the q|k|v boundaries, every store is
+// a 16-byte vector, and the per-row metadata (position, ring row) is read once per chunk instead of once per pair.  The
+// arithmetic is the same as epi_pair's, except that SiLU uses the hardware exp2/reciprocal (relative error ~1e-6, i.e. a
+// one-ulp bf16 flip in ~0.03 % of the gate values -- far below what the accumulation order already does).
+__device__ __forceinline__ uint32_t pack2_rn(float lo, float hi) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);  // one F2FP: .x (low half) = lo
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+__device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int MODE>
+__device__ __forceinline__ void epi_chunk32(const EpiParams& p, int t, int n, const uint32_t (&v)[32]) {
+  if constexpr (MODE == EPI_STORE || MODE == EPI_RESIDUAL) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (int64_t)t * p.ld_out + n);
+    uint32_t o[16];
+    if constexpr (MODE == EPI_RESIDUAL) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)t * p.ld_out + n);
+      uint4 r4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r4[q] = src[q];
+      const uint32_t* r = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        o[j] = pack2_rn(round_bf16(__uint_as_float(v[2 * j])) + bf16lo(r[j]), round_bf16(__uint_as_float(v[2 * j + 1])) + bf16hi(r[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = pack2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else if constexpr (MODE == EPI_F32) {
+    float4* dst = reinterpret_cast<float4*>(p.out_f32 + (int64_t)t * p.ld_out + n);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      dst[q] = make_float4(round_bf16(__uint_as_float(v[4 * q])), round_bf16(__uint_as_float(v[4 * q + 1])),
+                           round_bf16(__uint_as_float(v[4 * q + 2])), round_bf16(__uint_as_float(v[4 * q + 3])));
+  } else if constexpr (MODE == EPI_SWIGLU) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (int64_t)t * p.ld_out + (n >> 1));
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a0 = round_bf16(__uint_as_float(v[4 * j])), b0 = round_bf16(__uint_as_float(v[4 * j + 1]));
+      const float a1 = round_bf16(__uint_as_float(v[4 * j + 2])), b1 = round_bf16(__uint_as_float(v[4 * j + 3]));
+      o[j] = pack2_rn(round_bf16(fast_silu(a0)) * b0, round_bf16(fast_silu(a1)) * b1);
+    }
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else if constexpr (MODE == EPI_QKV_ROPE) {
+    uint32_t o[16];
+    uint16_t* dst;
+    uint16_t* ring = nullptr;
+    if (n < p.q_dim + p.kv_dim) {  // q or k: rotate the 16 interleaved pairs of this chunk
+      const int pos = p.positions[t];
+      const float4* cs4 = reinterpret_cast<const float4*>(p.rope + ((int64_t)pos * (kHeadDim / 2) + ((n & (kHeadDim - 1)) >> 1)) * 2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 cs = __ldg(cs4 + j);  // (cos, sin) of pairs 2j, 2j+1
+        float re, im;
+        ref_cmul(round_bf16(__uint_as_float(v[4 * j])), round_bf16(__uint_as_float(v[4 * j + 1])), cs.x, cs.y, re, im);
+        o[2 * j] = pack2_rn(re, im);
+        ref_cmul(round_bf16(__uint_as_float(v[4 * j + 2])), round_bf16(__uint_as_float(v[4 * j + 3])), cs.z, cs.w, re, im);
+        o[2 * j + 1] = pack2_rn(re, im);
+      }
+      if (n < p.q_dim) {
+        dst = reinterpret_cast<uint16_t*>(p.q_out) + (int64_t)t * p.q_dim + n;
+      } else {
+        dst = reinterpret_cast<uint16_t*>(p.k_out) + (int64_t)t * p.kv_dim + (n - p.q_dim);
+        if (p.cache_rows != nullptr) {
+          const int row = p.cache_rows[t];
+          if (row >= 0) ring = reinterpret_cast<uint16_t*>(p.cache_k) + (int64_t)row * p.kv_dim + (n - p.q_dim);
+        }
+      }
+    } else {  // v: stored as projected
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = pack2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      const int c = n - p.q_dim - p.kv_dim;
+      dst = reinterpret_cast<uint16_t*>(p.v_out) + (int64_t)t * p.kv_dim + c;
+      if (p.cache_rows != nullptr) {
+        const int row = p.cache_rows[t];
+        if (row >= 0) ring = reinterpret_cast<uint16_t*>(p.cache_v) + (int64_t)row * p.kv_dim + c;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(dst)[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    if (ring != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(ring)[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+  }
+}
+
 }  // namespace mb200

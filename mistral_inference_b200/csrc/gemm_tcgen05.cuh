@@ -41,6 +41,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// Same, delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -65,7 +82,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+// the same arrival on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
       "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -74,7 +97,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
         "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld_32x32b_x32_nowait(taddr, v);
+  tmem_wait_ld();
 }
 
 // Shared-memory matrix descriptor of a K-major, 128B-swizzled tile whose rows are 64 bf16 = 128 bytes:
@@ -85,7 +113,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kUmmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TG_BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
 
-template <int MODE>
+// CL = 2: thread-block clusters of two CTAs that work on vertically adjacent tiles (same W columns, consecutive 128-row blocks).
+// Each CTA fetches HALF of the shared [256 x 64] W tile and TMA-multicasts it into both shared memories, so the L2 -> SM traffic
+// per CTA and k-block drops from 48 KB to 32 KB (at T = 4096 the single-CTA kernel pulls ~20 TB/s out of L2).  A stage may be
+// refilled only when BOTH CTAs' MMAs have read it: the empty barriers count two commits, each multicast to the pair.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(TG_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -97,12 +129,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.T + TG_BM - 1) / TG_BM, num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cta = (int)blockIdx.x / CL, n_cta = (int)gridDim.x / CL;  // cluster index / clusters in the grid
+  // a cluster walks "super tiles" of CL vertically adjacent tiles; rows past T read as zeros (TMA) and are never stored
+  const int num_m = ((p.T + TG_BM - 1) / TG_BM + CL - 1) / CL, num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -114,7 +149,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TG_TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1)
+    cluster_sync_all();  // the peer's barriers must be initialised before any multicast copy or commit reaches them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -122,15 +160,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * TG_BM, n0 = (tile / num_m) * TG_BN;
+      for (int tile = cta; tile < num_tiles; tile += n_cta) {
+        const int m0 = ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const uint32_t s = it % TG_STAGES, par = (it / TG_STAGES) & 1;
           mbar_wait(&empty[s], par ^ 1, 11, it);
-          mbar_arrive_expect_tx(&full[s], TG_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[s], TG_STAGE_BYTES);  // A + both halves of W (the peer's half may land first: tx-count goes negative)
           uint8_t* sa = smem + s * TG_STAGE_BYTES;
           tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, m0);
-          tma_load_2d(sa + TG_A_BYTES, &map_w, &full[s], kb * TG_BK, n0);
+          if (CL > 1)
+            tma_load_2d_multicast(sa + TG_A_BYTES + rank * (TG_B_BYTES / CL), &map_w, &full[s], kb * TG_BK, n0 + rank * (TG_BN / CL),
+                                  (uint16_t)((1u << CL) - 1));
+          else
+            tma_load_2d(sa + TG_A_BYTES, &map_w, &full[s], kb * TG_BK, n0);
         }
       }
     }
@@ -138,7 +180,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       uint32_t it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+      for (int tile = cta; tile < num_tiles; tile += n_cta, ++acc_it) {
         const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_par ^ 1, 12, acc_it);  // the epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -152,7 +194,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TG_BK / 16; ++k)  // +32 bytes (= 2 in 16-byte units) per K = 16 step inside the 128-byte swizzled row
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kUmmaIdesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+          if (CL > 1)  // frees the stage in both CTAs (each producer writes into both) when these MMAs have read it
+            umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+          else
+            umma_commit(&empty[s]);
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete
       }
@@ -161,20 +206,24 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     // ================= epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =================
     const int lane_base = (warp & 3) * 32;
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
-      const int m0 = (tile % num_m) * TG_BM, n0 = (tile / num_m) * TG_BN;
+    for (int tile = cta; tile < num_tiles; tile += n_cta, ++acc_it) {
+      const int m0 = ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
       const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_par, 14, acc_it);
       tc_fence_after();
       const int t = m0 + lane_base + lane;
+      // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue
+      const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32_nowait(trow, va);
 #pragma unroll 1
-      for (int c = 0; c < TG_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN + c * 32, v);
-        if (t < p.T) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) epi_pair<MODE>(p.epi, t, n0 + c * 32 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        }
+      for (int c = 0; c < TG_BN / 32; c += 2) {
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32_nowait(trow + (c + 1) * 32, vb);
+        if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, va);
+        tmem_wait_ld();
+        if (c + 2 < TG_BN / 32) tmem_ld_32x32b_x32_nowait(trow + (c + 2) * 32, va);
+        if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + (c + 1) * 32, vb);
       }
       tc_fence_before();
       __syncwarp();
@@ -182,7 +231,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1)
+    cluster_sync_all();  // the peer's last commits still arrive on this CTA's barriers
+  else
+    __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TG_TMEM_COLS);
 }
 
@@ -225,12 +277,23 @@ inline bool tcgen05_gemm_eligible(int64_t T, int64_t N, int64_t K) {
   return !forced_mma && T >= TG_BM && N % TG_BN == 0 && K % TG_BK == 0;
 }
 
+// MB200_GEMM_CLUSTER=0 forces the single-CTA kernel
+inline bool tcgen05_cluster_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB200_GEMM_CLUSTER");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 template <int MODE>
 int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
+  const bool pair = tcgen05_cluster_enabled() && g.T >= 4 * TG_BM;
   CUtensorMap map_a, map_w;
   int rc = make_tensor_map_2d(&map_a, g.a, g.T, g.K, TG_BM);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, TG_BN);
+  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, pair ? TG_BN / 2 : TG_BN);
   if (rc) return rc;
   TcGemmParams p;
   p.T = g.T;
@@ -240,9 +303,28 @@ int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
   int dev = 0, sms = 0;
   MB_CHECK_CUDA(cudaGetDevice(&dev));
   MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (pair) {
+    const int supers = ceil_div(ceil_div(g.T, TG_BM), 2) * (g.N / TG_BN), pairs = sms / 2;
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)(supers < pairs ? supers : pairs));
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = TG_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<MODE, 2>, map_a, map_w, p));
+    MB_CHECK_LAUNCH("gemm_tcgen05_kernel<cluster 2>");
+    return MB200_OK;
+  }
   const int tiles = ceil_div(g.T, TG_BM) * (g.N / TG_BN);
-  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-  gemm_tcgen05_kernel<MODE><<<tiles < sms ? tiles : sms, TG_THREADS, TG_SMEM, stream>>>(map_a, map_w, p);
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  gemm_tcgen05_kernel<MODE, 1><<<tiles < sms ? tiles : sms, TG_THREADS, TG_SMEM, stream>>>(map_a, map_w, p);
   MB_CHECK_LAUNCH("gemm_tcgen05_kernel");
   return MB200_OK;
 }

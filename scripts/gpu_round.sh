@@ -30,8 +30,8 @@ for s in $STEPS; do
       ;;
     ncu:*)
       pat="${s#ncu:}"
-      MB200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:${pat}" -s 6 -c 4 -f -o "gpurun_out/prof_${pat//[^a-zA-Z0-9_]/_}" \
-        python bench.py --steps 2 --warmup 3 --prefill 2048 --layers 4 --no-cpu-baseline > "gpurun_out/ncu_${pat//[^a-zA-Z0-9_]/_}.log" 2>&1
+      MB200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:${pat}" -s "${NCU_SKIP:-0}" -c "${NCU_COUNT:-4}" -f -o "gpurun_out/prof_${pat//[^a-zA-Z0-9_]/_}" \
+        python bench.py --steps 2 --warmup 3 ${NCU_BENCH_ARGS:---prefill 4096 --layers 2} --no-cpu-baseline > "gpurun_out/ncu_${pat//[^a-zA-Z0-9_]/_}.log" 2>&1
       echo "ncu $pat exit $?"
       ;;
   esac

@@ -139,6 +139,32 @@ def test_gemm_against_cuda_core_gemm(ws):
     assert_bf16_close(out, _abi.test_gemm_naive(a, w).to(torch.bfloat16), what="gemm vs naive")
 
 
+def test_gemm_cluster_pair_matches_single_cta(ws):
+    """T >= 512 runs the 2-CTA cluster kernel (W tile multicast to the pair); 128-row slices of the same input run the
+    single-CTA kernel.  Rows are independent and accumulate in the same k order, so the two must agree bit for bit --
+    through the residual and the SiLU*mul epilogues, with a ragged last tile and an odd number of row tiles."""
+    T, dim, hid = 700, 1024, 1536
+    x, res = rnd(T, hid, seed=30).to(DEV), rnd(T, dim, seed=31).to(DEV)
+    w2 = rnd(dim, hid, seed=32, scale=hid ** -0.5).to(DEV)
+    out = torch.empty(T, dim, dtype=torch.bfloat16, device=DEV)
+    _abi.linear_residual(x, w2, res, out, ws)
+    xin = rnd(T, dim, seed=33).to(DEV)
+    w13 = rnd(2 * hid, dim, seed=34, scale=dim ** -0.5).to(DEV)
+    g = torch.empty(T, hid, dtype=torch.bfloat16, device=DEV)
+    _abi.ffn_gateup(xin, None, w13, g, 1e-5, ws)
+    for r0 in range(0, T, 128):
+        n = min(128, T - r0)
+        if n < 128:
+            r0 = T - 128  # the single-CTA tcgen05 kernel needs T >= 128
+            n = 128
+        o1 = torch.empty(n, dim, dtype=torch.bfloat16, device=DEV)
+        _abi.linear_residual(x[r0:r0 + n].contiguous(), w2, res[r0:r0 + n].contiguous(), o1, ws)
+        assert torch.equal(o1, out[r0:r0 + n]), f"residual epilogue rows {r0}.."
+        g1 = torch.empty(n, hid, dtype=torch.bfloat16, device=DEV)
+        _abi.ffn_gateup(xin[r0:r0 + n].contiguous(), None, w13, g1, 1e-5, ws)
+        assert torch.equal(g1, g[r0:r0 + n]), f"gate/up epilogue rows {r0}.."
+
+
 def _oracle_decode(q, ck, cv, kv_len, H, KV):
     rep = H // KV
     outs = []
