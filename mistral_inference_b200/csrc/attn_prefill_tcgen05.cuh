@@ -14,9 +14,10 @@
 
 namespace mb200 {
 
-constexpr int FA_BM = 128, FA_BN = 128, FA_THREADS = 192, FA_STAGES = 3;
+constexpr int FA_BM = 128, FA_BN = 128, FA_THREADS = 320, FA_STAGES = 3;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int FA_TILE_BYTES = 128 * kHeadDim * 2;  // one [128 x 128] bf16 tile = two swizzled [128 x 64] boxes = 32 KB
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 1024 + 256;
+constexpr int FA_XCH_BYTES = 2 * 2 * FA_BM * 4;  // row max / row sum exchange between the two softmax threads of a row, double buffered
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 128 /*barriers*/ + FA_XCH_BYTES;  // 231,552 of 232,448 bytes
 constexpr int FA_COL_S = 0 /* two buffers: 0 and 128 */, FA_COL_O = 256, FA_COL_P = 384, FA_TMEM_COLS = 512;
 
 struct FaParams {
@@ -64,8 +65,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(FA_THREADS, 1)
     attn_prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                 const __grid_constant__ CUtensorMap map_v, const FaParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // SW128 tiles want 1024-byte alignment; there is no room left to pad by hand
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + FA_TILE_BYTES;  // stage s: K at sKV + s*2*TILE, V right after
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES));
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint64_t* p_full = bars + 9;           // softmax (4 warps) -> MMA
   uint64_t* pv_done = bars + 10;         // MMA (commit) -> softmax: the PV product of a tile has finished reading P / writing O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* xch = reinterpret_cast<float*>(smem + FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 128);  // [2 buffers][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.z, g = h / (p.H / p.KV);
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);  // one arrive per softmax warp
     mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -159,8 +162,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       }
     }
   } else {
-    // ================= softmax warps: thread = query row =================
+    // ================= softmax warps: two threads per query row =================
+    // Warps 2..5 and 6..9 each cover the 128 TMEM lanes (a warp may touch lanes 32*(warp%4)..+31); the first group takes score
+    // columns 0..63 of every tile, the second 64..127, and the same halves of O.  The row maximum is exchanged through shared
+    // memory (one named barrier per tile); each thread keeps the partial row sum of its own columns.
     const int lane_base = (warp & 3) * 32;
+    const int half = (warp - 2) >> 2;     // which 64 columns
     const int r = lane_base + lane;       // row in the tile = TMEM lane
     const int i = i0 + r;                 // local query index; position == i (first prefill: seqpos = 0)
     const bool row_valid = i < s_len;
@@ -169,19 +176,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     for (int t = 0; t < n_tiles; ++t) {
       mbar_wait(&s_full[t & 1], (t >> 1) & 1, 25, t);
       tc_fence_after();
-      const int j0 = key_lo + t * FA_BN;
-      const uint32_t scol = trow + FA_COL_S + (t & 1) * 128;
+      const int j0 = key_lo + t * FA_BN + half * 64;
+      const uint32_t scol = trow + FA_COL_S + (t & 1) * 128 + half * 64;
       // Only edge tiles need per-element masks (tile-uniform test): the causal diagonal, the window's lower edge, the ragged
       // end of the sequence.  Interior tiles take the straight-line path.
-      const bool edge = (j0 + FA_BN - 1 > i0) || (j0 <= i0 + FA_BM - 1 - p.W) || (i0 + FA_BM > s_len);
+      const bool edge = (key_lo + t * FA_BN + FA_BN - 1 > i0) || (key_lo + t * FA_BN <= i0 + FA_BM - 1 - p.W) || (i0 + FA_BM > s_len);
       // the score row is read from TMEM ONCE and kept in registers for both passes
-      uint32_t sv[4][32];
+      uint32_t sv[2][32];
       float mraw = -3.0e38f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32_nowait(scol + c * 32, sv[c]);
+      tmem_ld_32x32b_x32_nowait(scol, sv[0]);
+      tmem_ld_32x32b_x32_nowait(scol + 32, sv[1]);
       tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         if (edge) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -195,6 +202,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           for (int e = 0; e < 32; ++e) mraw = fmaxf(mraw, __uint_as_float(sv[c][e]));
         }
       }
+      // exchange with the thread that holds the other 64 columns of this row (buffer t&1: its previous use was two tiles ago)
+      float* xb = xch + (t & 1) * 2 * FA_BM;
+      xb[half * FA_BM + r] = mraw;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mraw = fmaxf(mraw, xb[(half ^ 1) * FA_BM + r]);
       const float mx = fmaxf(m_run, mraw > -1.0e38f ? mraw * p.scale_log2 : -1.0e30f);
       const bool grew = mx > m_run;
       // P and O belong to the PV product of the previous tile until it has completed
@@ -202,34 +214,35 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         mbar_wait(pv_done, (t - 1) & 1, 27, t);
         tc_fence_after();
       }
-      // rescale O (TMEM) only when some row of this warp raised its maximum (after the first tiles that is rare)
+      // rescale O (TMEM) only when some row of this warp raised its maximum (after the first tiles that is rare); both threads of
+      // a row see the same maximum, so the two warps that share these rows take the same branch
       if (t > 0 && __any_sync(0xffffffffu, grew)) {
         const float corr = ex2_approx(m_run - mx);
         l_run *= corr;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(trow + FA_COL_O + c * 32, v);
+          tmem_ld_32x32b_x32(trow + FA_COL_O + half * 64 + c * 32, v);
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
-          tmem_st_32x32b_x32(trow + FA_COL_O + c * 32, v);
+          tmem_st_32x32b_x32(trow + FA_COL_O + half * 64 + c * 32, v);
         }
       }
       m_run = mx;
       // P = exp2(s * scale - m) as bf16 pairs -> TMEM (A operand of the PV product)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -mx));
           const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -mx));
           l_run += e0 + e1;
-          pk[e >> 1] = pack_bf16x2(e0, e1);
+          pk[e >> 1] = pack2_rn(e0, e1);
         }
         // 16 packed columns per chunk of 32 keys
         asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-                         trow + FA_COL_P + c * 16),
+                         trow + FA_COL_P + half * 32 + c * 16),
                      "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
                      "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
                      : "memory");
@@ -239,23 +252,28 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // final: O / l -> bf16 -> global (this thread's row: 256 contiguous bytes)
+    // final: O / l -> bf16 -> global (this thread's half row: 128 contiguous bytes).  The row sum is the sum of the two partial
+    // sums; the exchange uses the buffer the last tile did NOT use (its last readers passed the last tile's barrier).
+    float* xb = xch + (n_tiles & 1) * 2 * FA_BM;
+    xb[half * FA_BM + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_run += xb[(half ^ 1) * FA_BM + r];
     mbar_wait(pv_done, (n_tiles - 1) & 1, 26, 0);
     tc_fence_after();
     const float inv = row_valid ? 1.f / l_run : 0.f;
-    bf16* dst = p.out + (int64_t)(tok0 + i) * p.H * kHeadDim + (int64_t)h * kHeadDim;
+    bf16* dst = p.out + (int64_t)(tok0 + i) * p.H * kHeadDim + (int64_t)h * kHeadDim + half * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(trow + FA_COL_O + c * 32, v);
+      tmem_ld_32x32b_x32(trow + FA_COL_O + half * 64 + c * 32, v);
       if (row_valid) {
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv);
+          o.x = pack2_rn(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv);
+          o.y = pack2_rn(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
+          o.z = pack2_rn(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv);
+          o.w = pack2_rn(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv);
           *reinterpret_cast<uint4*>(dst + c * 32 + e) = o;
         }
       }
