@@ -259,7 +259,8 @@ def run_ours(a, rank: int, world: int):
     if rank != 0:
         return None
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
-    prefill_kernels = "gemm_tcgen05_kernel (tcgen05.mma/TMEM/TMA) + attn_prefill_kernel (mma.sync flash) + rmsnorm/kv_ring_write"
+    prefill_kernels = ("gemm_tcgen05_kernel (tcgen05.mma/TMEM/TMA, 2-CTA clusters with multicast W tiles) + attn_prefill_tcgen05_kernel "
+                       "(tcgen05 flash attention, S/P/O in TMEM) + rmsnorm/kv_ring_write")
     return {
         "metric": "decode tokens/sec (bf16, batch=1, seq=4k) [+ prefill TFLOPS, both vs roofline]",
         "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
