@@ -1,13 +1,14 @@
 // First-prefill attention (varlen, causal, sliding window; every key comes from the new chunk) on tcgen05 / TMEM / TMA.
 //
-// Roofline: tensor pipe.  CTA = (128-query tile, query head, sequence); 6 warps:
-//   warp 0    TMA producer: Q tile once, then K and V tiles of 128 keys into a 2-stage ring (128B-swizzled [128 x 64] boxes)
+// Roofline: tensor pipe / MUFU (one exp2 per score).  CTA = (query head, 128-query tile, sequence); 10 warps:
+//   warp 0    TMA producer: Q tile once, then K and V tiles of 128 keys into a 3-stage ring (128B-swizzled [128 x 64] boxes)
 //   warp 1    MMA issuer: S[128 x 128] = Q K^T (both operands K-major from shared memory), and after the softmax
 //             O[128 x 128] += P V with P read from TENSOR MEMORY (A operand) and V as an MN-major shared-memory operand
-//   warps 2-5 softmax: one thread per query row (TMEM lane): tcgen05.ld the score row, mask (causal + window + sequence end),
-//             online softmax in fp32, P -> bf16 -> tcgen05.st back into TMEM, rescale O in TMEM, final O / l -> bf16 -> global
+//   warps 2-9 softmax: two threads per query row (TMEM lane), 64 score columns each: tcgen05.ld the half row, mask (causal +
+//             window + sequence end; edge tiles only), online softmax in fp32 (row maximum exchanged through shared memory),
+//             P -> bf16 -> tcgen05.st back into TMEM, rescale O in TMEM when a maximum grew, final O / l -> bf16 -> global
 // TMEM columns: S buffer 0 0..127 | S buffer 1 128..255 | O 256..383 | P 384..447 (bf16 pairs).  S is double buffered so the
-// QK^T MMAs of tile t+1 run while the softmax warps work on tile t; the score row is read from TMEM once (128 registers).
+// QK^T MMAs of tile t+1 run while the softmax warps work on tile t; each score is read from TMEM once.
 // The mma.sync kernel (attn_prefill.cuh) remains for chunks that also read the ring (seqpos > 0) and for the cache-less mode.
 #pragma once
 #include "gemm_tcgen05.cuh"

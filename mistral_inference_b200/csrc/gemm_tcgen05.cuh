@@ -1,14 +1,17 @@
 // C[T, N] = A[T, K] * W[N, K]^T on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed.
 //
 // Roofline: tensor pipe (2*T*N*K flops).  Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled [128 x 64] A tile + [256 x 64] W tile per stage) -> 4-stage ring
-//   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M = 128, N = 256, K = 16 x 4 per stage); tcgen05.commit
-//            releases the shared-memory stage and, after the last k-block, publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld the 128 x 256 fp32 accumulator out of TMEM (two buffers of 256 columns, so the MMAs of the
-//            next tile overlap this one's epilogue) and run the same pair epilogues as every other linear (bf16 rounding,
-//            RoPE + ring scatter, SiLU*mul, residual add, fp32 logits)
+//   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled [128 x 64] A tile + [BN x 64] W tile per stage) -> 4- or 6-stage
+//            ring.  For T >= 512 the CTAs run as clusters of two on vertically adjacent tiles and each fetches half of the
+//            shared W tile, multicast into both shared memories (2/3 of the L2 -> SM traffic of the single-CTA kernel)
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M = 128, N = BN, K = 16 x 4 per stage); tcgen05.commit
+//            releases the shared-memory stage (in both CTAs of a pair) and, after the last k-block, publishes the accumulator
+//   warps 2-5 epilogue: one thread per output row reads the fp32 accumulator out of TMEM 32 columns at a time (two TMEM
+//            buffers, so the MMAs of the next tile overlap this one's epilogue; two register buffers, so the next tcgen05.ld
+//            overlaps this chunk's arithmetic) and runs the row-chunk epilogues of epilogue.cuh (bf16 rounding, then RoPE +
+//            ring scatter / SiLU*mul / residual add / fp32 logits) with 16-byte stores
 // Both operands are K-major ([rows, K] row-major): the canonical TN GEMM, no transposes anywhere.
-// Tiles are walked m-fastest so that the ~32 CTAs that share a W tile run together and hit it in L2.
+// Tiles are walked m-fastest so that the CTAs that share a W tile run together and hit it in L2.
 #pragma once
 #include <cuda.h>
 
@@ -23,12 +26,21 @@
 
 namespace mb200 {
 
-constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64;
 constexpr int TG_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
-constexpr int TG_A_BYTES = TG_BM * TG_BK * 2, TG_B_BYTES = TG_BN * TG_BK * 2;
-constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TG_TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;
+// The tile width BN is 256 (4 stages of 48 KB) or 128 (6 stages of 32 KB).  256 halves the W traffic per flop; 128 is chosen by
+// the launcher for problems too small to give every SM a 256-wide tile (and for N that is a multiple of 128 only).
+template <int BN>
+struct TgCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBBytes = BN * TG_BK * 2;
+  static constexpr int kStageBytes = TG_A_BYTES + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;  // 2 accumulator buffers x BN fp32 columns
+  // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+};
 
 struct TcGemmParams {
   int T, N, K;
@@ -110,16 +122,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kUmmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TG_BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
 
 // CL = 2: thread-block clusters of two CTAs that work on vertically adjacent tiles (same W columns, consecutive 128-row blocks).
 // Each CTA fetches HALF of the shared [256 x 64] W tile and TMA-multicasts it into both shared memories, so the L2 -> SM traffic
 // per CTA and k-block drops from 48 KB to 32 KB (at T = 4096 the single-CTA kernel pulls ~20 TB/s out of L2).  A stage may be
 // refilled only when BOTH CTAs' MMAs have read it: the empty barriers count two commits, each multicast to the pair.
-template <int MODE, int CL>
+template <int MODE, int CL, int BN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
+  using Cfg = TgCfg<BN>;
+  constexpr int TG_STAGES = Cfg::kStages, TG_B_BYTES = Cfg::kBBytes, TG_STAGE_BYTES = Cfg::kStageBytes, TG_TMEM_COLS = Cfg::kTmemCols;
+  constexpr int TG_BN = BN;
+  constexpr uint32_t kUmmaIdesc = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 wants 1024-B tiles
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
@@ -274,42 +288,40 @@ inline bool tcgen05_gemm_eligible(int64_t T, int64_t N, int64_t K) {
     const char* e = getenv("MB200_GEMM");
     forced_mma = (e != nullptr && e[0] == 'm') ? 1 : 0;
   }
-  return !forced_mma && T >= TG_BM && N % TG_BN == 0 && K % TG_BK == 0;
+  return !forced_mma && T >= TG_BM && N % 128 == 0 && K % TG_BK == 0;
 }
 
-// MB200_GEMM_CLUSTER=0 forces the single-CTA kernel
+// MB200_GEMM_CLUSTER=0 forces the single-CTA kernel; MB200_GEMM_BN=128|256 forces the tile width.  Read at every launch
+// (a getenv is ~100 ns) so the tests can switch variants inside one process.
 inline bool tcgen05_cluster_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("MB200_GEMM_CLUSTER");
-    on = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return on != 0;
+  const char* e = getenv("MB200_GEMM_CLUSTER");
+  return !(e != nullptr && e[0] == '0');
+}
+inline int tcgen05_forced_bn() {
+  const char* e = getenv("MB200_GEMM_BN");
+  return e != nullptr ? atoi(e) : 0;
 }
 
-template <int MODE>
-int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
-  const bool pair = tcgen05_cluster_enabled() && g.T >= 4 * TG_BM;
+template <int MODE, int BN>
+int launch_gemm_tcgen05_bn(const GemmParams& g, bool pair, int sms, cudaStream_t stream) {
+  using Cfg = TgCfg<BN>;
   CUtensorMap map_a, map_w;
   int rc = make_tensor_map_2d(&map_a, g.a, g.T, g.K, TG_BM);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, pair ? TG_BN / 2 : TG_BN);
+  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, pair ? BN / 2 : BN);
   if (rc) return rc;
   TcGemmParams p;
   p.T = g.T;
   p.N = g.N;
   p.K = g.K;
   p.epi = g.epi;
-  int dev = 0, sms = 0;
-  MB_CHECK_CUDA(cudaGetDevice(&dev));
-  MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (pair) {
-    const int supers = ceil_div(ceil_div(g.T, TG_BM), 2) * (g.N / TG_BN), pairs = sms / 2;
-    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+    const int supers = ceil_div(ceil_div(g.T, TG_BM), 2) * (g.N / BN), pairs = sms / 2;
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * (unsigned)(supers < pairs ? supers : pairs));
     cfg.blockDim = dim3(TG_THREADS);
-    cfg.dynamicSmemBytes = TG_SMEM;
+    cfg.dynamicSmemBytes = Cfg::kSmem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -318,15 +330,32 @@ int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<MODE, 2>, map_a, map_w, p));
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<MODE, 2, BN>, map_a, map_w, p));
     MB_CHECK_LAUNCH("gemm_tcgen05_kernel<cluster 2>");
     return MB200_OK;
   }
-  const int tiles = ceil_div(g.T, TG_BM) * (g.N / TG_BN);
-  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-  gemm_tcgen05_kernel<MODE, 1><<<tiles < sms ? tiles : sms, TG_THREADS, TG_SMEM, stream>>>(map_a, map_w, p);
+  const int tiles = ceil_div(g.T, TG_BM) * (g.N / BN);
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  gemm_tcgen05_kernel<MODE, 1, BN><<<tiles < sms ? tiles : sms, TG_THREADS, Cfg::kSmem, stream>>>(map_a, map_w, p);
   MB_CHECK_LAUNCH("gemm_tcgen05_kernel");
   return MB200_OK;
+}
+
+template <int MODE>
+int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
+  const bool pair = tcgen05_cluster_enabled() && g.T >= 4 * TG_BM;
+  int dev = 0, sms = 0;
+  MB_CHECK_CUDA(cudaGetDevice(&dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // 128-wide tiles only when 256-wide ones cannot fill the machine once (small T or N).  Measured at T = 4096: narrowing the
+  // N = 4096 GEMMs (512 tiles = 3.46 rounds -> 1024 tiles = 6.9 rounds) makes them SLOWER (wo+w2 237 -> 343 us on average):
+  // per flop the narrow tile pulls 1.5x the bytes out of L2, and that, not tile quantisation, is the binding limit there.
+  const int units = pair ? sms / 2 : sms, m_units = pair ? ceil_div(ceil_div(g.T, TG_BM), 2) : ceil_div(g.T, TG_BM);
+  const bool narrow_auto = g.N % 256 != 0 || (int64_t)m_units * (g.N / 256) < units;
+  bool narrow = narrow_auto;
+  if (tcgen05_forced_bn() == 128) narrow = true;
+  if (tcgen05_forced_bn() == 256 && g.N % 256 == 0) narrow = false;
+  return narrow ? launch_gemm_tcgen05_bn<MODE, 128>(g, pair, sms, stream) : launch_gemm_tcgen05_bn<MODE, 256>(g, pair, sms, stream);
 }
 
 }  // namespace mb200

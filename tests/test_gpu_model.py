@@ -143,6 +143,25 @@ def test_forward_without_cache():
     assert d.max() <= LOGIT_ATOL
 
 
+@pytest.mark.parametrize("over,lens", [
+    ({}, [700]),                          # one long sequence: 2-CTA cluster GEMMs (T >= 512) + tcgen05 flash attention, ragged last tile
+    ({"sliding_window": 200}, [640, 300]),  # two sequences, window shorter than the prompt: window edge tiles + ring wrap on write
+])
+def test_long_first_prefill_vs_oracle(over, lens):
+    """The tensor-core prefill kernels at model level: a first prefill long enough for the tcgen05 GEMM (cluster pairs, row-chunk
+    epilogues: RoPE + ring scatter, residual, SiLU*mul, fp32 logits) and the tcgen05 attention, against the CPU oracle on the
+    same weights; then one decode step off the cache that prefill wrote."""
+    p = synth.shape("tiny", **over)
+    m, om = gpu_model(p, len(lens)), oracle_model(p, len(lens))
+    toks = torch.tensor(synth.synth_prompt(sum(lens), p["vocab_size"], 11))
+    cache, ocache = new_cache(m, max(lens) + 8), om.new_cache(max(lens) + 8)
+    d = report(f"long first prefill {over} {lens}", m.forward(toks.cuda(), lens, cache), om.forward(toks, lens, ocache))
+    assert d.max() <= LOGIT_ATOL and d.mean() <= 0.004
+    nxt = torch.tensor([3 + b for b in range(len(lens))])
+    d = report(f"decode after long prefill {over} {lens}", m.forward(nxt.cuda(), [1] * len(lens), cache), om.forward(nxt, [1] * len(lens), ocache))
+    assert d.max() <= LOGIT_ATOL
+
+
 def test_sampling_path_runs():
     p = synth.shape("tiny")
     m = gpu_model(p, 2)

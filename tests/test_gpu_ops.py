@@ -139,10 +139,13 @@ def test_gemm_against_cuda_core_gemm(ws):
     assert_bf16_close(out, _abi.test_gemm_naive(a, w).to(torch.bfloat16), what="gemm vs naive")
 
 
-def test_gemm_cluster_pair_matches_single_cta(ws):
+@pytest.mark.parametrize("bn", ["128", "256"])
+def test_gemm_cluster_pair_matches_single_cta(ws, bn, monkeypatch):
     """T >= 512 runs the 2-CTA cluster kernel (W tile multicast to the pair); 128-row slices of the same input run the
     single-CTA kernel.  Rows are independent and accumulate in the same k order, so the two must agree bit for bit --
-    through the residual and the SiLU*mul epilogues, with a ragged last tile and an odd number of row tiles."""
+    through the residual and the SiLU*mul epilogues, with a ragged last tile and an odd number of row tiles, for both tile
+    widths (the launcher picks the width per shape; MB200_GEMM_BN pins it here)."""
+    monkeypatch.setenv("MB200_GEMM_BN", bn)
     T, dim, hid = 700, 1024, 1536
     x, res = rnd(T, hid, seed=30).to(DEV), rnd(T, dim, seed=31).to(DEV)
     w2 = rnd(dim, hid, seed=32, scale=hid ** -0.5).to(DEV)
@@ -152,6 +155,9 @@ def test_gemm_cluster_pair_matches_single_cta(ws):
     w13 = rnd(2 * hid, dim, seed=34, scale=dim ** -0.5).to(DEV)
     g = torch.empty(T, hid, dtype=torch.bfloat16, device=DEV)
     _abi.ffn_gateup(xin, None, w13, g, 1e-5, ws)
+    # against the CUDA-core GEMM (independent of every tcgen05 code path)
+    assert_bf16_close(out, (res.float() + _abi.test_gemm_naive(x, w2).to(torch.bfloat16).float()).to(torch.bfloat16),
+                      atol=2 * 2 ** -8 * res.abs().max().item(), what="cluster gemm + residual vs naive")
     for r0 in range(0, T, 128):
         n = min(128, T - r0)
         if n < 128:
@@ -163,6 +169,14 @@ def test_gemm_cluster_pair_matches_single_cta(ws):
         g1 = torch.empty(n, hid, dtype=torch.bfloat16, device=DEV)
         _abi.ffn_gateup(xin[r0:r0 + n].contiguous(), None, w13, g1, 1e-5, ws)
         assert torch.equal(g1, g[r0:r0 + n]), f"gate/up epilogue rows {r0}.."
+    # the other tile width and the single-CTA kernel at full T give the same bits
+    monkeypatch.setenv("MB200_GEMM_BN", "256" if bn == "128" else "128")
+    out2 = torch.empty_like(out)
+    _abi.linear_residual(x, w2, res, out2, ws)
+    assert torch.equal(out2, out), "tile widths disagree"
+    monkeypatch.setenv("MB200_GEMM_CLUSTER", "0")
+    _abi.linear_residual(x, w2, res, out2, ws)
+    assert torch.equal(out2, out), "cluster and single-CTA kernels disagree"
 
 
 def _oracle_decode(q, ck, cv, kv_len, H, KV):
