@@ -29,15 +29,17 @@ namespace mb200 {
 constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64;
 constexpr int TG_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;
-// The tile width BN is 256 (4 stages of 48 KB) or 128 (6 stages of 32 KB).  256 halves the W traffic per flop; 128 is chosen by
-// the launcher for problems too small to give every SM a 256-wide tile (and for N that is a multiple of 128 only).
+// The tile width BN is 256 (4 stages of 48 KB), 192 (4 stages of 40 KB) or 128 (6 stages of 32 KB).  256 has the least W traffic
+// per flop; 128 is chosen by the launcher for problems too small to give every SM a 256-wide tile (and for N that is a multiple
+// of 128 only); 192 only for N that is a multiple of 192 but not of 128.  Narrower tiles to even out the last round of the
+// persistent schedule were measured and lose: L2 -> SM bandwidth per flop, not tile quantisation, is what binds at T = 4096.
 template <int BN>
 struct TgCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = BN == 128 ? 6 : 4;
   static constexpr int kBBytes = BN * TG_BK * 2;
   static constexpr int kStageBytes = TG_A_BYTES + kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BN;  // 2 accumulator buffers x BN fp32 columns
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // 2 accumulator buffers x BN fp32 columns, allocated as a power of two
   // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
 };
@@ -288,10 +290,10 @@ inline bool tcgen05_gemm_eligible(int64_t T, int64_t N, int64_t K) {
     const char* e = getenv("MB200_GEMM");
     forced_mma = (e != nullptr && e[0] == 'm') ? 1 : 0;
   }
-  return !forced_mma && T >= TG_BM && N % 128 == 0 && K % TG_BK == 0;
+  return !forced_mma && T >= TG_BM && (N % 128 == 0 || N % 192 == 0) && K % TG_BK == 0;
 }
 
-// MB200_GEMM_CLUSTER=0 forces the single-CTA kernel; MB200_GEMM_BN=128|256 forces the tile width.  Read at every launch
+// MB200_GEMM_CLUSTER=0 forces the single-CTA kernel; MB200_GEMM_BN=128|192|256 forces the tile width.  Read at every launch
 // (a getenv is ~100 ns) so the tests can switch variants inside one process.
 inline bool tcgen05_cluster_enabled() {
   const char* e = getenv("MB200_GEMM_CLUSTER");
@@ -351,10 +353,16 @@ int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
   // N = 4096 GEMMs (512 tiles = 3.46 rounds -> 1024 tiles = 6.9 rounds) makes them SLOWER (wo+w2 237 -> 343 us on average):
   // per flop the narrow tile pulls 1.5x the bytes out of L2, and that, not tile quantisation, is the binding limit there.
   const int units = pair ? sms / 2 : sms, m_units = pair ? ceil_div(ceil_div(g.T, TG_BM), 2) : ceil_div(g.T, TG_BM);
-  const bool narrow_auto = g.N % 256 != 0 || (int64_t)m_units * (g.N / 256) < units;
-  bool narrow = narrow_auto;
-  if (tcgen05_forced_bn() == 128) narrow = true;
-  if (tcgen05_forced_bn() == 256 && g.N % 256 == 0) narrow = false;
+  int bn = 256;
+  if (g.N % 256 != 0 || (int64_t)m_units * (g.N / 256) < units) {
+    bn = g.N % 128 == 0 ? 128 : 192;
+  }
+  // 192-wide tiles (N = 6144: 5.19 rounds of 256 -> 6.92 rounds at 3/4 of the cost) were measured too: qkv+RoPE at T = 4096
+  // 156 -> 169 us, slower for the same reason.  They stay available for N that is a multiple of 192 only and for the tests.
+  const int forced = tcgen05_forced_bn();
+  if ((forced == 128 || forced == 192 || forced == 256) && g.N % forced == 0) bn = forced;
+  if (bn == 192) return launch_gemm_tcgen05_bn<MODE, 192>(g, pair, sms, stream);
+  const bool narrow = bn == 128;
   return narrow ? launch_gemm_tcgen05_bn<MODE, 128>(g, pair, sms, stream) : launch_gemm_tcgen05_bn<MODE, 256>(g, pair, sms, stream);
 }
 

@@ -139,14 +139,14 @@ def test_gemm_against_cuda_core_gemm(ws):
     assert_bf16_close(out, _abi.test_gemm_naive(a, w).to(torch.bfloat16), what="gemm vs naive")
 
 
-@pytest.mark.parametrize("bn", ["128", "256"])
+@pytest.mark.parametrize("bn", ["128", "192", "256"])
 def test_gemm_cluster_pair_matches_single_cta(ws, bn, monkeypatch):
     """T >= 512 runs the 2-CTA cluster kernel (W tile multicast to the pair); 128-row slices of the same input run the
     single-CTA kernel.  Rows are independent and accumulate in the same k order, so the two must agree bit for bit --
     through the residual and the SiLU*mul epilogues, with a ragged last tile and an odd number of row tiles, for both tile
     widths (the launcher picks the width per shape; MB200_GEMM_BN pins it here)."""
     monkeypatch.setenv("MB200_GEMM_BN", bn)
-    T, dim, hid = 700, 1024, 1536
+    T, dim, hid = 700, 1536, 1536  # N = 1536 / 3072: multiples of all three tile widths
     x, res = rnd(T, hid, seed=30).to(DEV), rnd(T, dim, seed=31).to(DEV)
     w2 = rnd(dim, hid, seed=32, scale=hid ** -0.5).to(DEV)
     out = torch.empty(T, dim, dtype=torch.bfloat16, device=DEV)
@@ -169,14 +169,44 @@ def test_gemm_cluster_pair_matches_single_cta(ws, bn, monkeypatch):
         g1 = torch.empty(n, hid, dtype=torch.bfloat16, device=DEV)
         _abi.ffn_gateup(xin[r0:r0 + n].contiguous(), None, w13, g1, 1e-5, ws)
         assert torch.equal(g1, g[r0:r0 + n]), f"gate/up epilogue rows {r0}.."
-    # the other tile width and the single-CTA kernel at full T give the same bits
-    monkeypatch.setenv("MB200_GEMM_BN", "256" if bn == "128" else "128")
+    # the other tile widths and the single-CTA kernel at full T give the same bits
     out2 = torch.empty_like(out)
-    _abi.linear_residual(x, w2, res, out2, ws)
-    assert torch.equal(out2, out), "tile widths disagree"
+    for other in ("128", "192", "256"):
+        monkeypatch.setenv("MB200_GEMM_BN", other)
+        _abi.linear_residual(x, w2, res, out2, ws)
+        assert torch.equal(out2, out), f"tile widths {bn} and {other} disagree"
     monkeypatch.setenv("MB200_GEMM_CLUSTER", "0")
     _abi.linear_residual(x, w2, res, out2, ws)
     assert torch.equal(out2, out), "cluster and single-CTA kernels disagree"
+
+
+def test_qkv_rope_epilogue_same_bits_for_every_tile_width(ws, rope, monkeypatch):
+    """Fused QKV + RoPE + ring scatter at Mistral-7B width (N = 6144 = 24 x 256 = 32 x 192 = 48 x 128) through the 2-CTA
+    cluster kernel: the three tile widths must produce identical q / k / v and identical cache rows."""
+    T, dim, H, KV, hd = 640, 4096, 32, 8, 128
+    x = rnd(T, dim, seed=40).to(DEV)
+    nw = (1 + 0.2 * rnd(dim, seed=41).float()).to(torch.bfloat16).to(DEV)
+    wqkv = rnd((H + 2 * KV) * hd, dim, seed=42, scale=dim ** -0.5).to(DEV)
+    positions = (torch.arange(T, dtype=torch.int32) * 3 % 8000).to(DEV)
+    rows = torch.tensor([t if t % 5 else -1 for t in range(T)], dtype=torch.int32).to(DEV)
+    _, table_dev = rope
+    outs = {}
+    for bn in ("256", "192", "128"):
+        monkeypatch.setenv("MB200_GEMM_BN", bn)
+        q = torch.empty(T, H * hd, dtype=torch.bfloat16, device=DEV)
+        k = torch.empty(T, KV * hd, dtype=torch.bfloat16, device=DEV)
+        v = torch.empty_like(k)
+        ck = torch.zeros(T, KV, hd, dtype=torch.bfloat16, device=DEV)
+        cv = torch.zeros_like(ck)
+        _abi.attn_qkv(x, nw, wqkv, table_dev, positions, q, k, v, ck, cv, rows, H, KV, hd, 1e-5, ws)
+        torch.cuda.synchronize()
+        outs[bn] = (q, k, v, ck, cv)
+    for bn in ("192", "128"):
+        for a, b, what in zip(outs["256"], outs[bn], ("q", "k", "v", "cache_k", "cache_v")):
+            assert torch.equal(a, b), f"{what}: tile width {bn} differs from 256"
+    q, k, v, ck, cv = outs["192"]
+    keep = rows >= 0
+    assert torch.equal(ck[rows[keep].long()].reshape(-1, KV * hd), k[keep]) and torch.equal(cv[rows[keep].long()].reshape(-1, KV * hd), v[keep])
 
 
 def _oracle_decode(q, ck, cv, kv_len, H, KV):
