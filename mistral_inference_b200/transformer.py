@@ -9,7 +9,7 @@ import logging
 import math
 import os
 from pathlib import Path
-from typing import Any, Dict, List, Mapping, Optional, Union
+from typing import Any, Dict, List, Mapping, Optional, Tuple, Union
 
 import torch
 from torch import nn
@@ -33,9 +33,17 @@ class _OutputView:
 
 
 class Transformer(nn.Module):
-    def __init__(self, args: TransformerArgs, pipeline_rank: int = 0, num_pipeline_ranks: int = 1, softmax_fp32: bool = True):
+    def __init__(self, args: TransformerArgs, pipeline_rank: int = 0, num_pipeline_ranks: int = 1, softmax_fp32: bool = True,
+                 expert_parallel: Optional[Tuple[int, int]] = None, expert_group: Any = None):
+        """Same signature as the reference (transformer.py:34-40) plus `expert_parallel = (rank, world)`: MoE experts sharded
+        `e % world == rank` over the ranks of `expert_group` (default process group), everything else replicated, one
+        all-reduce of [T, dim] per MoE layer."""
         super().__init__()
         self.args = args
+        self.expert_parallel = expert_parallel or (0, 1)
+        assert 0 <= self.expert_parallel[0] < self.expert_parallel[1], self.expert_parallel
+        assert self.expert_parallel[1] == 1 or (args.moe is not None and num_pipeline_ranks == 1), \
+            "expert sharding needs a MoE model and excludes pipeline ranks"
         self.vocab_size = args.vocab_size
         self.n_layers = args.n_layers
         self._rope_table: Optional[torch.Tensor] = None
@@ -60,7 +68,8 @@ class Transformer(nn.Module):
         end = min(self.n_layers, offset + num_layers_per_rank)
         self.layers = nn.ModuleDict({
             str(i): TransformerBlock(dim=args.dim, hidden_dim=args.hidden_dim, n_heads=args.n_heads, n_kv_heads=args.n_kv_heads,
-                                     head_dim=args.head_dim, norm_eps=args.norm_eps, lora=args.lora, moe=args.moe)
+                                     head_dim=args.head_dim, norm_eps=args.norm_eps, lora=args.lora, moe=args.moe,
+                                     expert_shard=self.expert_parallel, expert_group=expert_group)
             for i in range(offset, end)
         })
         self.n_local_layers = len(self.layers)
@@ -212,7 +221,8 @@ class Transformer(nn.Module):
         return host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
 
     def _megakernel_ok(self, B: int) -> bool:
-        return (B == 1 and self.num_pipeline_ranks == 1 and self.args.n_kv_heads <= 8 and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
+        return (B == 1 and self.num_pipeline_ranks == 1 and self.expert_parallel[1] == 1 and self.args.n_kv_heads <= 8
+                and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
                 and (self.args.moe is None or (self.args.moe.num_experts <= 32 and self.args.moe.num_experts_per_tok <= 4)))
 
     def _decode_megakernel(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
@@ -236,8 +246,8 @@ class Transformer(nn.Module):
                 else:  # the kernel reads the expert tables instead
                     w13p = w2p = 0
                     gate_tab.append(ff.gate_weight.data_ptr())
-                    w13_tab += [ex.w13.data_ptr() for ex in ff.experts]
-                    w2_tab += [ex.w2_weight.data_ptr() for ex in ff.experts]
+                    w13_tab += [ff.experts[str(e)].w13.data_ptr() for e in range(E)]
+                    w2_tab += [ff.experts[str(e)].w2_weight.data_ptr() for e in range(E)]
                 desc[i] = [blk.attention.wqkv.data_ptr(), blk.attention.wo_weight.data_ptr(), w13p, w2p,
                            blk.attention_norm.weight.data_ptr(), blk.ffn_norm.weight.data_ptr(), cache.cache_k[i].data_ptr(),
                            cache.cache_v[i].data_ptr()]
@@ -358,7 +368,9 @@ class Transformer(nn.Module):
                     raise ValueError(f"Unexpected key {k}")
                 ff = blk.feed_forward
                 if parts[1] == "experts":
-                    ff = ff.experts[int(parts[2])]
+                    if parts[2] not in ff.experts:
+                        return False  # an expert owned by another expert-parallel rank
+                    ff = ff.experts[parts[2]]
                     parts = parts[2:]
                 name = parts[1]
                 if name == "w1":
@@ -371,6 +383,19 @@ class Transformer(nn.Module):
                     raise ValueError(f"Unexpected key {k}")
         else:
             raise ValueError(f"Unexpected key {k}")
+        return True
+
+    def _owns_key(self, k: str) -> bool:
+        """False for checkpoint tensors that belong to another pipeline / expert-parallel rank (decided from the key alone, so a
+        loader can skip reading them)."""
+        if not k.startswith("layers."):
+            return True
+        _, lid, rest = k.split(".", 2)
+        if lid not in self.layers:
+            return False
+        parts = rest.split(".")
+        if len(parts) > 2 and parts[0] == "feed_forward" and parts[1] == "experts":
+            return parts[2] in self.layers[lid].feed_forward.experts
         return True
 
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False) -> None:  # type: ignore[override]
@@ -407,7 +432,7 @@ class Transformer(nn.Module):
             ff = blk.feed_forward
             if hasattr(ff, "experts"):
                 out[p + "feed_forward.gate.weight"] = ff.gate_weight
-                for e, ex in enumerate(ff.experts):
+                for e, ex in ff.experts.items():  # keyed by the global expert id; the local ones only when sharded
                     for n in ("w1", "w2", "w3"):
                         out[p + f"feed_forward.experts.{e}.{n}.weight"] = getattr(ex, n).weight
             else:
@@ -421,8 +446,9 @@ class Transformer(nn.Module):
     @staticmethod
     def from_folder(folder: Union[Path, str], max_batch_size: int = 1, num_pipeline_ranks: int = 1,
                     device: Union[torch.device, str] = "cuda", dtype: Optional[torch.dtype] = None,
-                    softmax_fp32: bool = True) -> "Transformer":
-        """transformer.py:297-338.  Tensors stream from disk straight into the packed device buffers."""
+                    softmax_fp32: bool = True, expert_parallel: Optional[Tuple[int, int]] = None, expert_group: Any = None) -> "Transformer":
+        """transformer.py:297-338.  Tensors stream from disk straight into the packed device buffers; with `expert_parallel`
+        the experts of other ranks are skipped (never read into device memory)."""
         with open(Path(folder) / "params.json", "r") as f:
             model_args = TransformerArgs.from_dict(json.load(f))
         model_args.max_batch_size = max_batch_size
@@ -437,7 +463,8 @@ class Transformer(nn.Module):
         if dev.type == "cuda" and dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         with torch.device(dev):
-            model = Transformer(model_args, pipeline_rank=pipeline_rank, num_pipeline_ranks=num_pipeline_ranks, softmax_fp32=softmax_fp32)
+            model = Transformer(model_args, pipeline_rank=pipeline_rank, num_pipeline_ranks=num_pipeline_ranks, softmax_fp32=softmax_fp32,
+                                expert_parallel=expert_parallel, expert_group=expert_group)
         if pt_model_file.exists():
             loaded = torch.load(str(pt_model_file), mmap=True)
             ck_dtype = next(iter(loaded.values())).dtype
@@ -453,7 +480,7 @@ class Transformer(nn.Module):
                 loaded_keys = set()
                 with torch.no_grad():
                     for k in keys:
-                        if model._assign(k, f.get_tensor(k)):
+                        if model._owns_key(k) and model._assign(k, f.get_tensor(k)):
                             loaded_keys.add(k)
                 missing = set(model.reference_keys()) - loaded_keys
                 assert not missing, f"missing keys: {sorted(missing)[:8]}"

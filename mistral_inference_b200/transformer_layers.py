@@ -6,7 +6,7 @@ include/mistral_b200.h); weights are stored pre-packed for the fused kernels:
   FeedForward.w13 [2 * hidden, dim], row 2i = w1[i], row 2i+1 = w3[i]  (SiLU*mul in the epilogue)
 `wq/wk/wv/w1/w3` are exposed as zero-copy views for state-dict compatibility.
 """
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 from torch import nn
@@ -151,7 +151,7 @@ class TransformerBlock(nn.Module):
     """transformer_layers.py:123-169: pre-norm residual wiring; FeedForward or MoeLayer."""
 
     def __init__(self, dim: int, hidden_dim: int, n_heads: int, n_kv_heads: int, head_dim: int, norm_eps: float,
-                 lora: Optional[LoraArgs] = None, moe: Optional[MoeArgs] = None):
+                 lora: Optional[LoraArgs] = None, moe: Optional[MoeArgs] = None, expert_shard: Tuple[int, int] = (0, 1), expert_group=None):
         super().__init__()
         self.n_heads = n_heads
         self.dim = dim
@@ -161,8 +161,10 @@ class TransformerBlock(nn.Module):
         self.ffn_norm = RMSNorm(dim, eps=norm_eps)
         self.feed_forward: nn.Module
         if moe is not None:
-            self.feed_forward = MoeLayer(experts=[FeedForward(dim=dim, hidden_dim=hidden_dim, lora=lora) for _ in range(moe.num_experts)],
-                                         gate_weight=nn.Parameter(torch.empty(moe.num_experts, dim), requires_grad=False), moe_args=moe)
+            g, G = expert_shard  # this rank allocates only the experts it owns (e % G == g): SURVEY.md 8(e)
+            self.feed_forward = MoeLayer(experts={e: FeedForward(dim=dim, hidden_dim=hidden_dim, lora=lora) for e in range(moe.num_experts) if e % G == g},
+                                         gate_weight=nn.Parameter(torch.empty(moe.num_experts, dim), requires_grad=False), moe_args=moe,
+                                         expert_shard=expert_shard, expert_group=expert_group)
         else:
             self.feed_forward = FeedForward(dim=dim, hidden_dim=hidden_dim, lora=lora)
 

@@ -56,3 +56,55 @@ def test_replicas_timing_rule_and_pipeline_split_world2():
     assert v0 == v1 == 2 * 1 * 50 * 1000.0 / 125.0   # whole-job tokens/s, weak scaling
     assert l0 == ["0", "1"] and l1 == ["2", "3"]
     assert emb0 and not emb1 and head1 and not head0
+
+
+def _moe_worker(rank: int, world: int, port: int, q):
+    """Expert-sharded MoE on CPU: the product's routing/combination code with the oracle's FeedForward as the
+    expert function and a gloo all-reduce, against the oracle's unsharded MoE (moe.py:24-32)."""
+    sys.path.insert(0, str(REPO))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn.functional as F
+
+    import mistral_inference_b200 as mi
+    from mistral_inference_b200 import synth
+    from mistral_inference_b200.moe import all_reduce_partial, route_and_combine
+    from mistral_inference_b200.transformer import Transformer
+    from oracle import restatement as R
+
+    p = synth.shape("tiny-moe")
+    E, k, dim = p["moe"]["num_experts"], p["moe"]["num_experts_per_tok"], p["dim"]
+    sd = synth.synth_state_dict(p, 3)
+    experts = [tuple(sd[f"layers.0.feed_forward.experts.{e}.{n}.weight"] for n in ("w1", "w2", "w3")) for e in range(E)]
+    gate_w = sd["layers.0.feed_forward.gate.weight"]
+    x = synth.synth_tensor("x", (37, dim), 5, torch.bfloat16, "cpu")
+    want = R.moe_forward(x, gate_w, experts, k)
+    local = [e for e in range(E) if e % world == rank]
+    got = route_and_combine(x, F.linear(x, gate_w), k, local, lambda e, rows: R.feed_forward(rows, *experts[e]),
+                            lambda r: all_reduce_partial(r))
+    # key filtering of the sharded model: this rank holds the router, all attention weights and only its own experts
+    args = mi.TransformerArgs.from_dict(dict(p))
+    m = Transformer(args, expert_parallel=(rank, world)).to(torch.bfloat16)
+    m.load_state_dict(sd)
+    held = sorted({int(key.split(".")[4]) for key in m.state_dict() if ".experts." in key})
+    q.put((rank, bool(torch.equal(got, want)), float((got.float() - want.float()).abs().max()), held, m._megakernel_ok(1),
+           m._owns_key("layers.0.feed_forward.experts.%d.w1.weight" % ((rank + 1) % world)), "layers.0.feed_forward.gate.weight" in m.state_dict()))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_expert_sharded_moe_world2_matches_unsharded_oracle():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_moe_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, equal, worst, held, mega, owns_other, has_gate in res:
+        assert equal, f"rank {rank}: sharded MoE differs from the unsharded oracle by {worst}"  # top-2: bf16(a + b) in any order
+        assert held == [e for e in range(8) if e % 2 == rank]
+        assert not mega and not owns_other and has_gate  # sharded decode goes through the per-op path with the all-reduce
