@@ -19,7 +19,6 @@ import shutil
 import statistics
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 from pathlib import Path
@@ -143,7 +142,7 @@ def build_gpu_model(p: dict, max_batch: int, seed: int = 0):
 
 def run_ours(a, rank: int, world: int):
     import mistral_inference_b200 as mi  # noqa: F401
-    from mistral_inference_b200 import _abi
+    from mistral_inference_b200 import _abi  # noqa: F401  (loads libmb200.so now: a missing build fails here, loudly)
     from mistral_inference_b200.cache import BufferCache
 
     p = synth.shape(a.model)

@@ -15,7 +15,7 @@ Folder layout is the reference's on-disk contract (transformer.py:297-336): `par
 import json
 import zlib
 from pathlib import Path
-from typing import Dict, Iterator, Optional, Tuple, Union
+from typing import Dict, Iterator, Tuple, Union
 
 import torch
 

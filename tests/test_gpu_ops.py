@@ -9,7 +9,6 @@ cancellation can be many ulps of the (small) result -- those get an absolute tol
 Attention outputs get `atol` for near-zero values, and the prefill kernel 2 ulp because P is rounded to bf16 before the
 PV tensor-core product (as in any tensor-core attention).
 """
-import math
 
 import pytest
 import torch
