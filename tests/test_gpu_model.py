@@ -191,6 +191,8 @@ def test_full_size_7b_layer_properties():
     ("tiny-moe", {}, 9, 10),                                  # in-kernel router + experts (moe.py:24-32)
     ("tiny-moe", {"sliding_window": 5}, 12, 8),
     ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 40, 4),  # real expert shapes: 2 x (8 experts x 176 M params)
+    ("mistral-nemo-12b", {"n_layers": 2, "vocab_size": 4096}, 140, 4),  # BASELINE config 3 shape: dim 5120 != H*hd, no window
+    ("mixtral-8x22b", {"n_layers": 2, "vocab_size": 4096}, 40, 3),      # BASELINE config 5 shape: H/KV = 6, dim 6144, hidden 16384
 ])
 def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
     """The persistent one-kernel-per-token decode step against (a) the per-op kernel path and (b) the CPU oracle."""
