@@ -130,6 +130,37 @@ int mb200_ffn_gateup(const void* x, const void* norm_w, const void* w13, void* g
 int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* logits, int64_t T, int64_t dim,
                   int64_t vocab, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side step state of the batched decode loop.  Replaces BufferCache.get_input_metadata for one-token steps
+ * (cache.py:197-263: positions, cache_positions, the padded-keys mask's kv_seqlen) and update_seqlens
+ * (cache.py:191-192) with one tiny kernel, so a CUDA graph of the decode step replays without host writes.
+ *   seqpos_dev [B] int32 (DEVICE, in/out): tokens cached so far per sequence; incremented by one.
+ *   meta_dev   [3B + 1 + n_windows * 2B] int32 (DEVICE, out):
+ *              positions[B] | q_start[B+1] | seqpos[B] | per distinct window W: cache_rows[B] (= pos %% W + b*W), kv_len[B]
+ *   windows_host [n_windows] int32 (HOST array, n_windows <= 8): the distinct cache sizes (cache.py:13-24), ascending.
+ */
+int mb200_decode_meta(int32_t* seqpos_dev, int32_t* meta_dev, int64_t B, const int32_t* windows_host, int64_t n_windows,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Token selection and log-probabilities on the device (the per-token tail of generate()).
+ *   logits [T, vocab] fp32 (the lm head's output), one CTA per row, nothing of size [T, vocab] is written.
+ * mb200_argmax_rows:    out[t] = argmax(logits[t]) with the first index on ties -- `sample` with temperature == 0
+ *                       (generate.py:154-158).
+ * mb200_logprob_gather: out[t] = log_softmax(logits[t])[target[t]] in fp32 (generate.py:101-117,134-135); rows with
+ *                       target[t] < 0 are skipped.
+ * mb200_sample_top_p:   one draw per row from softmax(logits / temperature) restricted to the nucleus: a token is kept iff
+ *                       the probability mass of the tokens ranked before it is <= top_p (generate.py:151-170; the reference
+ *                       hard-codes top_p = 0.8, :126).  uniform [T] fp32 in [0, 1) supplies the randomness (torch.rand on the
+ *                       device keeps torch.manual_seed semantics); the draw is the inverse CDF over the kept tokens in index
+ *                       order -- same distribution as torch.multinomial on the sorted vector, not the same stream.
+ *   out / target: int64 device arrays.
+ */
+int mb200_argmax_rows(const float* logits, int64_t* out_dev, int64_t T, int64_t vocab, void* stream);
+int mb200_logprob_gather(const float* logits, const int64_t* target_dev, float* out_dev, int64_t T, int64_t vocab, void* stream);
+int mb200_sample_top_p(const float* logits, const float* uniform_dev, int64_t* out_dev, int64_t T, int64_t vocab,
+                       float temperature, float top_p, void* stream);
+
 /* Upper bound of the scratch any entry point above needs for up to T tokens of this geometry. */
 size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
                              int64_t hidden, int64_t vocab, int64_t max_batch);

@@ -37,6 +37,10 @@ _SIGNATURES = {
                                  c_void_p]),
     "mb200_lm_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t,
                               c_void_p]),
+    "mb200_decode_meta": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mb200_argmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "mb200_logprob_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "mb200_sample_top_p": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p]),
     "mb200_workspace_bytes": (c_size_t, [c_int64] * 8),
     "mb200_decode_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, c_int64, c_void_p,
@@ -171,6 +175,39 @@ def lm_head(x, norm_w, w_out, logits, eps, ws: Workspace) -> None:
     T, dim = x.shape
     _check(lib().mb200_lm_head(_ptr(x), _ptr(norm_w), _ptr(w_out), _ptr(logits), T, dim, w_out.shape[0], eps, ws.ptr, ws.nbytes,
                                _stream()), "mb200_lm_head")
+
+
+def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    T, V = logits.shape
+    assert logits.dtype == torch.float32
+    out = torch.empty(T, dtype=torch.long, device=logits.device) if out is None else out
+    _check(lib().mb200_argmax_rows(_ptr(logits), _ptr(out), T, V, _stream()), "mb200_argmax_rows")
+    return out
+
+
+def logprob_gather(logits: torch.Tensor, target: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """log_softmax(logits, -1)[t, target[t]] (rows with target < 0 are left untouched)."""
+    T, V = logits.shape
+    assert logits.dtype == torch.float32 and target.dtype == torch.long and target.shape == (T,)
+    out = torch.zeros(T, dtype=torch.float32, device=logits.device) if out is None else out
+    _check(lib().mb200_logprob_gather(_ptr(logits), _ptr(target), _ptr(out), T, V, _stream()), "mb200_logprob_gather")
+    return out
+
+
+def sample_top_p(logits: torch.Tensor, uniform: torch.Tensor, temperature: float, top_p: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    T, V = logits.shape
+    assert logits.dtype == torch.float32 and uniform.dtype == torch.float32 and uniform.shape == (T,)
+    out = torch.empty(T, dtype=torch.long, device=logits.device) if out is None else out
+    _check(lib().mb200_sample_top_p(_ptr(logits), _ptr(uniform), _ptr(out), T, V, temperature, top_p, _stream()), "mb200_sample_top_p")
+    return out
+
+
+def decode_meta(seqpos_dev: torch.Tensor, meta_dev: torch.Tensor, windows) -> None:
+    """Device-side metadata of a one-token step for every sequence; advances `seqpos_dev` (include/mistral_b200.h)."""
+    B = seqpos_dev.shape[0]
+    arr = (ctypes.c_int32 * len(windows))(*[int(w) for w in windows])
+    assert seqpos_dev.dtype == torch.int32 and meta_dev.dtype == torch.int32 and meta_dev.numel() >= 3 * B + 1 + 2 * B * len(windows)
+    _check(lib().mb200_decode_meta(_ptr(seqpos_dev), _ptr(meta_dev), B, ctypes.cast(arr, c_void_p), len(windows), _stream()), "mb200_decode_meta")
 
 
 def decode_step(layers_dev, windows_dev, n_layers, emb, final_norm, w_out, rope, token_dev, pos, batch_row, logits, next_token, dim, hidden,

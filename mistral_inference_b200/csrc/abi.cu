@@ -8,6 +8,7 @@
 #include "elementwise.cuh"
 #include "gemm_mma.cuh"
 #include "gemm_tcgen05.cuh"
+#include "sampling.cuh"
 #include "skinny_linear.cuh"
 
 namespace mb200 {
@@ -117,6 +118,24 @@ int mb200_attn_qkv(const void* x, const void* norm_w, const void* wqkv, const fl
   e.kv_dim = (int)(n_kv_heads * head_dim);
   const int64_t N = (n_heads + 2 * n_kv_heads) * head_dim;
   return run_linear<EPI_QKV_ROPE>(x, norm_w, wqkv, e, T, N, dim, eps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mb200_decode_meta(int32_t* seqpos_dev, int32_t* meta_dev, int64_t B, const int32_t* windows_host, int64_t n_windows, void* stream) {
+  MB_CHECK_ARG(seqpos_dev && meta_dev && windows_host, "decode_meta: null pointer");
+  MB_CHECK_ARG(B >= 1 && n_windows >= 1 && n_windows <= kMaxWindows, "decode_meta: B=%lld, n_windows=%lld (max %d)", (long long)B,
+               (long long)n_windows, kMaxWindows);
+  DecodeMetaParams p;
+  p.seqpos = seqpos_dev;
+  p.meta = meta_dev;
+  p.B = (int)B;
+  p.n_w = (int)n_windows;
+  for (int j = 0; j < (int)n_windows; ++j) {
+    MB_CHECK_ARG(windows_host[j] >= 1, "decode_meta: window %d", (int)windows_host[j]);
+    p.windows[j] = windows_host[j];
+  }
+  decode_meta_kernel<<<(unsigned)ceil_div(B + 1, 128), 128, 0, (cudaStream_t)stream>>>(p);
+  MB_CHECK_LAUNCH("decode_meta_kernel");
+  return MB200_OK;
 }
 
 int mb200_kv_ring_write(const void* k_new, const void* v_new, void* cache_k, void* cache_v, const int32_t* cache_rows, int64_t T,
@@ -236,6 +255,34 @@ int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* l
   return run_linear<EPI_F32>(x, norm_w, w_out, e, T, vocab, dim, eps, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int mb200_argmax_rows(const float* logits, int64_t* out_dev, int64_t T, int64_t vocab, void* stream) {
+  MB_CHECK_ARG(logits && out_dev && T >= 0 && vocab >= 1, "argmax_rows: bad arguments");
+  if (T == 0) return MB200_OK;
+  argmax_rows_kernel<<<(unsigned)T, SP_THREADS, 0, (cudaStream_t)stream>>>(logits, (long long*)out_dev, (int)vocab);
+  MB_CHECK_LAUNCH("argmax_rows_kernel");
+  return MB200_OK;
+}
+
+int mb200_logprob_gather(const float* logits, const int64_t* target_dev, float* out_dev, int64_t T, int64_t vocab, void* stream) {
+  MB_CHECK_ARG(logits && target_dev && out_dev && T >= 0 && vocab >= 1, "logprob_gather: bad arguments");
+  if (T == 0) return MB200_OK;
+  logprob_gather_kernel<<<(unsigned)T, SP_THREADS, 0, (cudaStream_t)stream>>>(logits, (const long long*)target_dev, out_dev, (int)vocab);
+  MB_CHECK_LAUNCH("logprob_gather_kernel");
+  return MB200_OK;
+}
+
+int mb200_sample_top_p(const float* logits, const float* uniform_dev, int64_t* out_dev, int64_t T, int64_t vocab, float temperature,
+                       float top_p, void* stream) {
+  MB_CHECK_ARG(logits && uniform_dev && out_dev && T >= 0 && vocab >= 1, "sample_top_p: bad arguments");
+  MB_CHECK_ARG(temperature > 0.f && top_p >= 0.f && top_p <= 1.f, "sample_top_p: temperature=%g must be > 0 and top_p=%g in [0, 1]",
+               (double)temperature, (double)top_p);
+  if (T == 0) return MB200_OK;
+  sample_top_p_kernel<<<(unsigned)T, SP_THREADS, 0, (cudaStream_t)stream>>>(logits, uniform_dev, (long long*)out_dev, (int)vocab,
+                                                                            1.0f / temperature, top_p);
+  MB_CHECK_LAUNCH("sample_top_p_kernel");
+  return MB200_OK;
+}
+
 int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows_dev, int64_t n_layers, const void* emb, const void* final_norm,
                       const void* w_out, const float* rope, const int64_t* token_dev, int64_t pos, int64_t batch_row, float* logits,
                       int64_t* next_token_dev, int64_t dim,
@@ -311,6 +358,12 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
       kvu = e2 ? atoi(e2) : 0;
     }
     p.kv_uncapped = kvu;
+    static int pre = -1;
+    if (pre < 0) {
+      const char* e3 = getenv("MB200_MK_PRELOAD");
+      pre = e3 ? atoi(e3) : 1;
+    }
+    p.preload = pre;
   }
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
 

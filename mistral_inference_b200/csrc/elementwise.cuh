@@ -52,4 +52,38 @@ __global__ void kv_ring_write_kernel(const uint4* __restrict__ k_new, const uint
   }
 }
 
+// Device-side step state of the batched decode loop (replaces cache.py:197-263 for one-token steps).  Reads the
+// per-sequence positions, writes the metadata block every layer's kernels read -- same layout as the host-built block of
+// mistral_inference_b200/cache.py::build_metadata_host for seqlens = [1] * B:
+//   positions[B] | q_start[B + 1] | seqpos[B] | per distinct window W: cache_rows[B], kv_len[B]
+// -- and advances the positions, so a captured CUDA graph replays correct metadata without any host write.
+constexpr int kMaxWindows = 8;
+struct DecodeMetaParams {
+  int32_t* seqpos;  // [B] tokens cached so far (in/out: incremented)
+  int32_t* meta;    // [3B + 1 + n_w * 2B]
+  int B, n_w;
+  int windows[kMaxWindows];
+};
+__global__ void decode_meta_kernel(const DecodeMetaParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > p.B) return;
+  int32_t* q_start = p.meta + p.B;
+  if (b == p.B) {
+    q_start[b] = p.B;
+    return;
+  }
+  const int pos = p.seqpos[b];
+  p.meta[b] = pos;
+  q_start[b] = b;
+  p.meta[2 * p.B + 1 + b] = pos;
+  int32_t* o = p.meta + 3 * p.B + 1;
+  for (int j = 0; j < p.n_w; ++j) {
+    const int W = p.windows[j];
+    o[b] = pos % W + b * W;             // cache.py:235
+    o[p.B + b] = min(pos + 1, W);       // cache.py:250-254: kv_seqlen = (seqpos + 1).clamp(max = W)
+    o += 2 * p.B;
+  }
+  p.seqpos[b] = pos + 1;
+}
+
 }  // namespace mb200

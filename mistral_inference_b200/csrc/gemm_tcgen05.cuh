@@ -33,13 +33,21 @@ constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;
 // per flop; 128 is chosen by the launcher for problems too small to give every SM a 256-wide tile (and for N that is a multiple
 // of 128 only); 192 only for N that is a multiple of 192 but not of 128.  Narrower tiles to even out the last round of the
 // persistent schedule were measured and lose: L2 -> SM bandwidth per flop, not tile quantisation, is what binds at T = 4096.
-template <int BN>
+// TA = rows of the A (token) box.  128 for prefill.  For small batches (decode with 5..64 tokens) the box is 32 or 64 rows:
+// the MMA still has M = 128 and reads 16 KB from the A tile's base, i.e. it runs into whatever follows the tile in shared
+// memory -- accumulator row i depends on A row i only, and rows >= T are never stored.  The stage shrinks to (TA + BN) * 128
+// bytes, so the ring gets deep enough (16-20 stages) to keep a whole SM's share of HBM bandwidth in flight: those launches are
+// weight-streaming GEMMs, bound by HBM, with BN chosen by the launcher to give every SM at most one (equal) tile per round.
+template <int BN, int TA = 128>
 struct TgCfg {
-  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr int kABytes = TA * TG_BK * 2;
   static constexpr int kBBytes = BN * TG_BK * 2;
-  static constexpr int kStageBytes = TG_A_BYTES + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // 2 accumulator buffers x BN fp32 columns, allocated as a power of two
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSlack = TA < 128 ? TG_A_BYTES : 0;  // the last stage's M = 128 read must stay inside the allocation
+  static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - kSlack) / kStageBytes;
+  static constexpr int kStages = (TA < 128 || BN < 128) ? (kMaxStages > 24 ? 24 : kMaxStages) : (BN == 128 ? 6 : 4);
+  static constexpr int kSmem = kStages * kStageBytes + kSlack + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // 2 accumulators
   // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
 };
@@ -129,16 +137,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Each CTA fetches HALF of the shared [256 x 64] W tile and TMA-multicasts it into both shared memories, so the L2 -> SM traffic
 // per CTA and k-block drops from 48 KB to 32 KB (at T = 4096 the single-CTA kernel pulls ~20 TB/s out of L2).  A stage may be
 // refilled only when BOTH CTAs' MMAs have read it: the empty barriers count two commits, each multicast to the pair.
-template <int MODE, int CL, int BN>
+template <int MODE, int CL, int BN, int TA = 128>
 __global__ void __launch_bounds__(TG_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
-  using Cfg = TgCfg<BN>;
+  static_assert(TA == 128 || CL == 1, "small-batch variant is single-CTA");
+  using Cfg = TgCfg<BN, TA>;
   constexpr int TG_STAGES = Cfg::kStages, TG_B_BYTES = Cfg::kBBytes, TG_STAGE_BYTES = Cfg::kStageBytes, TG_TMEM_COLS = Cfg::kTmemCols;
+  constexpr int TG_A_BYTES = Cfg::kABytes;  // shadows the 128-row constant
   constexpr int TG_BN = BN;
   constexpr uint32_t kUmmaIdesc = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 wants 1024-B tiles
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES + Cfg::kSlack);
   uint64_t* empty = full + TG_STAGES;
   uint64_t* tmem_full = empty + TG_STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
@@ -232,14 +242,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
       const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN;
       uint32_t va[32], vb[32];
       tmem_ld_32x32b_x32_nowait(trow, va);
+      if constexpr (TG_BN == 32) {
+        tmem_wait_ld();
+        if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0, va);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < TG_BN / 32; c += 2) {
-        tmem_wait_ld();
-        tmem_ld_32x32b_x32_nowait(trow + (c + 1) * 32, vb);
-        if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, va);
-        tmem_wait_ld();
-        if (c + 2 < TG_BN / 32) tmem_ld_32x32b_x32_nowait(trow + (c + 2) * 32, va);
-        if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + (c + 1) * 32, vb);
+        for (int c = 0; c < TG_BN / 32; c += 2) {
+          tmem_wait_ld();
+          tmem_ld_32x32b_x32_nowait(trow + (c + 1) * 32, vb);
+          if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, va);
+          tmem_wait_ld();
+          if (c + 2 < TG_BN / 32) tmem_ld_32x32b_x32_nowait(trow + (c + 2) * 32, va);
+          if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + (c + 1) * 32, vb);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -290,7 +305,9 @@ inline bool tcgen05_gemm_eligible(int64_t T, int64_t N, int64_t K) {
     const char* e = getenv("MB200_GEMM");
     forced_mma = (e != nullptr && e[0] == 'm') ? 1 : 0;
   }
-  return !forced_mma && T >= TG_BM && (N % 128 == 0 || N % 192 == 0) && K % TG_BK == 0;
+  if (forced_mma || K % TG_BK != 0) return false;
+  if (T >= TG_BM) return N % 128 == 0 || N % 192 == 0;
+  return N % 32 == 0;  // small-batch weight-streaming variant (T <= 64 uses short A boxes; 65..127 the 128-row box)
 }
 
 // MB200_GEMM_CLUSTER=0 forces the single-CTA kernel; MB200_GEMM_BN=128|192|256 forces the tile width.  Read at every launch
@@ -343,12 +360,69 @@ int launch_gemm_tcgen05_bn(const GemmParams& g, bool pair, int sms, cudaStream_t
   return MB200_OK;
 }
 
+// ---- small-batch (decode, T < 128) launcher: weight-streaming, HBM-bound ------------------------------------------------------
+// One M tile; the N tiles are dealt to persistent CTAs.  BN is chosen so that the rounds of the persistent schedule are as full
+// as possible (every CTA streams the same number of weight rows), preferring wider tiles (bigger TMA boxes) on ties.
+inline int tcgen05_small_bn(int64_t N, int sms) {
+  const int forced = tcgen05_forced_bn();
+  if ((forced == 32 || forced == 64 || forced == 128 || forced == 256) && N % forced == 0) return forced;
+  int best = 0;
+  double best_score = -1.0;
+  const int cand[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (N % bn != 0) continue;
+    const int64_t tiles = N / bn, rounds = (tiles + sms - 1) / sms;
+    double score = (double)tiles / (double)(rounds * sms);
+    if (tiles < sms / 2) score *= 0.5;  // too few SMs pulling: per-SM ingest, not HBM, would bind
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int MODE, int BN, int TA>
+int launch_gemm_tcgen05_small_bn(const GemmParams& g, int sms, cudaStream_t stream) {
+  using Cfg = TgCfg<BN, TA>;
+  CUtensorMap map_a, map_w;
+  int rc = make_tensor_map_2d(&map_a, g.a, g.T, g.K, TA);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, BN);
+  if (rc) return rc;
+  TcGemmParams p;
+  p.T = g.T;
+  p.N = g.N;
+  p.K = g.K;
+  p.epi = g.epi;
+  const int tiles = g.N / BN;
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, 1, BN, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  gemm_tcgen05_kernel<MODE, 1, BN, TA><<<tiles < sms ? tiles : sms, TG_THREADS, Cfg::kSmem, stream>>>(map_a, map_w, p);
+  MB_CHECK_LAUNCH("gemm_tcgen05_kernel<small batch>");
+  return MB200_OK;
+}
+
+template <int MODE, int TA>
+int launch_gemm_tcgen05_small_ta(const GemmParams& g, int sms, cudaStream_t stream) {
+  switch (tcgen05_small_bn(g.N, sms)) {
+    case 256: return launch_gemm_tcgen05_small_bn<MODE, 256, TA>(g, sms, stream);
+    case 128: return launch_gemm_tcgen05_small_bn<MODE, 128, TA>(g, sms, stream);
+    case 64: return launch_gemm_tcgen05_small_bn<MODE, 64, TA>(g, sms, stream);
+    case 32: return launch_gemm_tcgen05_small_bn<MODE, 32, TA>(g, sms, stream);
+    default: return fail(MB200_E_INVALID, "small-batch GEMM: N=%d is not a multiple of 32", g.N);
+  }
+}
+
 template <int MODE>
 int launch_gemm_tcgen05(const GemmParams& g, cudaStream_t stream) {
   const bool pair = tcgen05_cluster_enabled() && g.T >= 4 * TG_BM;
   int dev = 0, sms = 0;
   MB_CHECK_CUDA(cudaGetDevice(&dev));
   MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (g.T <= 32) return launch_gemm_tcgen05_small_ta<MODE, 32>(g, sms, stream);
+  if (g.T <= 64) return launch_gemm_tcgen05_small_ta<MODE, 64>(g, sms, stream);
+  if (g.T < TG_BM) return launch_gemm_tcgen05_small_ta<MODE, 128>(g, sms, stream);
   // 128-wide tiles only when 256-wide ones cannot fill the machine once (small T or N).  Measured at T = 4096: narrowing the
   // N = 4096 GEMMs (512 tiles = 3.46 rounds -> 1024 tiles = 6.9 rounds) makes them SLOWER (wo+w2 237 -> 343 us on average):
   // per flop the narrow tile pulls 1.5x the bytes out of L2, and that, not tile quantisation, is the binding limit there.

@@ -75,7 +75,8 @@ class Transformer(nn.Module):
         self.n_local_layers = len(self.layers)
         self._ws: Optional[_abi.Workspace] = None
         self._ws_tokens = 0
-        self._decode_graphs: Dict[Any, Any] = {}
+        self.last_argmax: Optional[torch.Tensor] = None  # device token id(s) written by the last fused-argmax decode step
+        self._last_static_logits = 0                     # data_ptr of the logits buffer that argmax belongs to
 
     # ------------------------------------------------------------------ properties
     @property
@@ -110,8 +111,7 @@ class Transformer(nn.Module):
             a = self.args
             need = _abi.workspace_bytes(num_tokens, a.dim, a.n_heads, a.n_kv_heads, a.head_dim, a.hidden_dim, a.vocab_size,
                                         max(a.max_batch_size, 1))
-            self._decode_graphs = {}  # captured graphs hold the old workspace pointer
-            self._ws = _abi.Workspace(need, self.device)
+            self._ws = _abi.Workspace(need, self.device)  # decode states remember the pointer they captured (see _decode_state)
             self._ws_tokens = num_tokens
         return self._ws
 
@@ -134,6 +134,7 @@ class Transformer(nn.Module):
 
         input_metadata: Optional[List[CacheInputMetadata]] = None
         if cache is not None:
+            self._check_positions(cache, seqlens)
             input_metadata = cache.get_input_metadata(seqlens)
             positions = input_metadata[0].positions
         else:
@@ -197,6 +198,7 @@ class Transformer(nn.Module):
         ws = self.workspace(num_toks)
         if cache is not None:
             if input_metadata is None:
+                self._check_positions(cache, seqlens)
                 input_metadata = cache.get_input_metadata(seqlens)
             positions = input_metadata[0].positions
         else:
@@ -209,6 +211,13 @@ class Transformer(nn.Module):
             h = layer(h, rope, positions, view, ws)
         return h
 
+    def _check_positions(self, cache: BufferCache, seqlens: List[int]) -> None:
+        """The reference indexes freqs_cis[positions] and raises past the table (transformer.py:199); the kernels would read out of bounds."""
+        host = cache._kv_seqlens_host or [0] * len(seqlens)
+        last = max(p + s for p, s in zip(host, seqlens)) if seqlens else 0
+        if last > ROPE_TABLE_LEN:
+            raise IndexError(f"position {last - 1} is out of bounds for the rope table of {ROPE_TABLE_LEN} positions")
+
     # ------------------------------------------------------------------ CUDA-graph decode
     def _graph_decode_ok(self, seqlens: List[int], cache: Optional[BufferCache]) -> bool:
         if cache is None or self.num_pipeline_ranks != 1:
@@ -218,22 +227,34 @@ class Transformer(nn.Module):
         if os.environ.get("MB200_DECODE_GRAPH", "1") == "0":
             return False
         host = cache._kv_seqlens_host
-        return host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
+        return (host is not None and len(host) == len(seqlens) and host[0] != 0 and all(s == 1 for s in seqlens)
+                and len(set(cache.cache_sizes)) <= 8)
 
     def _megakernel_ok(self, B: int) -> bool:
         return (B == 1 and self.num_pipeline_ranks == 1 and self.expert_parallel[1] == 1 and self.args.n_kv_heads <= 8
                 and os.environ.get("MB200_MEGAKERNEL", "1") != "0"
                 and (self.args.moe is None or (self.args.moe.num_experts <= 32 and self.args.moe.num_experts_per_tok <= 4)))
 
+    def _decode_state(self, cache: BufferCache, key: Any) -> Dict[str, Any]:
+        """Per-(cache, kind) decode state (descriptor tables, static buffers, captured graph).  It lives ON THE CACHE OBJECT, so
+        it is freed with the cache (generate() allocates a cache per call); an entry is rebuilt when this model's workspace was
+        reallocated since (a captured graph holds the old pointer)."""
+        states = cache.__dict__.setdefault("_mb200_decode_states", {})
+        ws_ptr = self._ws.ptr if self._ws is not None else 0
+        st = states.get((id(self), key))
+        if st is None or st["ws_ptr"] != ws_ptr or st["device"] != self.device:
+            st = {"ws_ptr": ws_ptr, "device": self.device}
+            states[(id(self), key)] = st
+        return st
+
     def _decode_megakernel(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
         """Batch-1 decode step as ONE persistent cooperative kernel (csrc/decode_megakernel.cuh)."""
         import numpy as np
 
         a = self.args
-        key = ("mk", id(cache))
-        st = self._decode_graphs.get(key)
         ws = self.workspace(1)
-        if st is None or st["cache"] is not cache:
+        st = self._decode_state(cache, "mk")
+        if "layers" not in st:
             blocks = list(self.layers.values())
             desc = np.zeros((len(blocks), 8), dtype=np.uint64)
             moe = self.args.moe
@@ -252,18 +273,18 @@ class Transformer(nn.Module):
                            blk.attention_norm.weight.data_ptr(), blk.ffn_norm.weight.data_ptr(), cache.cache_k[i].data_ptr(),
                            cache.cache_v[i].data_ptr()]
             tab = lambda v: torch.tensor(v, dtype=torch.int64, device=self.device) if v else None  # noqa: E731
-            st = {"cache": cache, "E": E, "k": moe.num_experts_per_tok if moe is not None else 0,
-                  "moe_gate": tab(gate_tab), "moe_w13": tab(w13_tab), "moe_w2": tab(w2_tab),
-                  "layers": torch.from_numpy(desc.view(np.int64)).to(self.device),
-                  "windows": torch.tensor(cache.cache_sizes, dtype=torch.int32, device=self.device),
-                  "token": torch.zeros(1, dtype=torch.long, device=self.device),
-                  "next": torch.zeros(1, dtype=torch.long, device=self.device),
-                  "logits": torch.empty(1, self.vocab_size, dtype=torch.float32, device=self.device)}
-            self._decode_graphs[key] = st
+            st.update({"E": E, "k": moe.num_experts_per_tok if moe is not None else 0,
+                       "moe_gate": tab(gate_tab), "moe_w13": tab(w13_tab), "moe_w2": tab(w2_tab),
+                       "layers": torch.from_numpy(desc.view(np.int64)).to(self.device),
+                       "windows": torch.tensor(cache.cache_sizes, dtype=torch.int32, device=self.device),
+                       "token": torch.zeros(1, dtype=torch.long, device=self.device),
+                       "next": torch.zeros(1, dtype=torch.long, device=self.device),
+                       "logits": torch.empty(1, self.vocab_size, dtype=torch.float32, device=self.device)})
         if cache._kv_seqlens_host is None:
             cache.init_kvseqlens(1)
         pos = cache._kv_seqlens_host[0]
-        assert pos < self.rope_table.shape[0]
+        if pos >= ROPE_TABLE_LEN:
+            raise IndexError(f"position {pos} is out of bounds for the rope table of {ROPE_TABLE_LEN} positions")
         # `tokens` may be the previous step's fused argmax (st["next"]): then nothing is copied and the greedy loop is one
         # kernel launch per token
         tok = tokens.reshape(1)
@@ -275,43 +296,50 @@ class Transformer(nn.Module):
                          self.rope_table, tok, pos, 0, st["logits"], st["next"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
                          self.vocab_size, a.norm_eps, ws, st["E"], st["k"], st["moe_gate"], st["moe_w13"], st["moe_w2"])
         cache.update_seqlens([1])
+        self._last_static_logits = st["logits"].data_ptr()
         return st["logits"]
 
     def decode_static(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
-        """One decode step for every sequence of `cache` (one new token each) replayed from a CUDA graph: the ~5
-        kernels per layer are enqueued with a single graph launch instead of ~165 Python->C calls.  Returns the
-        graph's STATIC fp32 logits buffer [B, V] (overwritten by the next step).  The first call per
-        (cache, batch) runs eagerly (warm-up), the second captures."""
+        """One decode step for every sequence of `cache` (one new token each).  Batch 1: the persistent megakernel.  Batch > 1:
+        the per-layer kernels replayed from a CUDA graph.  The step state lives on the DEVICE: `mb200_decode_meta` derives
+        positions / ring rows / kv lengths from a device-side position vector and advances it inside the graph, so a replay
+        needs no host write at all (a pinned staging buffer rewritten by the host while earlier copies are still queued was the
+        round-1 design and a race).  Returns the STATIC fp32 logits buffer [B, V] (overwritten by the next step).  The first call
+        per (cache, batch) runs eagerly (warm-up: loads modules, sets function attributes), the second captures."""
         B = tokens.shape[0]
         if self._megakernel_ok(B):
             return self._decode_megakernel(tokens, cache)
         seqlens = [1] * B
-        key = (id(cache), B)
         self.workspace(B)
-        st = self._decode_graphs.get(key)
-        host, layout = cache.build_metadata_host(seqlens)
-        if st is None or st["cache"] is not cache:
-            # warm-up step, eager (also sets function attributes / loads modules outside of capture)
-            st = {"cache": cache, "graph": None,
-                  "tokens": torch.zeros(B, dtype=torch.long, device=self.device),
-                  "meta": torch.zeros(host.shape[0], dtype=torch.int32, device=self.device),
-                  "meta_host": torch.zeros(host.shape[0], dtype=torch.int32).pin_memory(),
-                  "logits": torch.empty(B, self.vocab_size, dtype=torch.float32, device=self.device)}
-            self._decode_graphs[key] = st
-        st["meta_host"].numpy()[:] = host
-        st["meta"].copy_(st["meta_host"], non_blocking=True)
-        st["tokens"].copy_(tokens, non_blocking=True)
+        st = self._decode_state(cache, ("graph", B))
+        host = cache._kv_seqlens_host
+        assert host is not None and len(host) == B, "decode_static needs a prefilled cache of this batch size"
+        if max(host) >= ROPE_TABLE_LEN:
+            raise IndexError(f"position {max(host)} is out of bounds for the rope table of {ROPE_TABLE_LEN} positions")
+        distinct = sorted(set(cache.cache_sizes))
+        if "meta" not in st:
+            st.update({"graph": None, "warmed": False, "expected": None,
+                       "seqpos": torch.zeros(B, dtype=torch.int32, device=self.device),
+                       "tokens": torch.zeros(B, dtype=torch.long, device=self.device),
+                       "meta": torch.zeros(3 * B + 1 + 2 * B * len(distinct), dtype=torch.int32, device=self.device),
+                       "logits": torch.empty(B, self.vocab_size, dtype=torch.float32, device=self.device),
+                       "next": torch.zeros(B, dtype=torch.long, device=self.device)})
+        if st["expected"] != host:  # another forward() advanced the cache since the last step (or this is the first one)
+            st["seqpos"].copy_(torch.tensor(host, dtype=torch.int32))  # pageable source: staged by the runtime, no reuse hazard
+        st["tokens"].copy_(tokens, non_blocking=True)  # device source (previous pick): D2D; host source: staged by the runtime
+        layout = {"T": B, "B": B, "prefill": False, "first_prefill": False, "max_seqlen": 1, "windows": distinct}
         md = cache.metadata_from_block(st["meta"], layout, seqlens)
 
         def run() -> None:
+            _abi.decode_meta(st["seqpos"], st["meta"], distinct)
             h = self._hidden_no_norm(st["tokens"], seqlens, cache, md)
             _abi.lm_head(h, self.norm.weight, self.output_weight, st["logits"], self.args.norm_eps, self.workspace(B))
+            _abi.argmax_rows(st["logits"], st["next"])  # greedy pick on the device (generate.py:156): feeds the next step
 
-        if st["graph"] is None and not st.get("warmed"):
+        if st["graph"] is None and not st["warmed"]:
             run()
             st["warmed"] = True
         elif st["graph"] is None:
-            self.workspace(B)  # allocate outside of capture
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 run()
@@ -320,7 +348,58 @@ class Transformer(nn.Module):
         else:
             st["graph"].replay()
         cache.update_seqlens(seqlens)
+        st["expected"] = list(cache._kv_seqlens_host)
+        self.last_argmax = st["next"]
+        self._last_static_logits = st["logits"].data_ptr()
         return st["logits"]
+
+    # ------------------------------------------------------------------ generate() support
+    def last_argmax_valid_for(self, logits: torch.Tensor) -> bool:
+        """True when `last_argmax` is the decode kernel's own argmax of exactly this logits buffer."""
+        return self.last_argmax is not None and logits.data_ptr() == self._last_static_logits
+
+    @torch.inference_mode()
+    def next_token_logits(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
+        """fp32 logits [B, V] of one decode step for every sequence.  On the single-stage CUDA path this is the step's static
+        buffer (no clone; valid until the next step), otherwise `forward`."""
+        B = tokens.shape[0]
+        if self.pipeline_rank == self.num_pipeline_ranks - 1 == 0 and self._graph_decode_ok([1] * B, cache):
+            self._check_runnable()
+            return self.decode_static(tokens, cache)
+        self._last_static_logits = 0
+        out = self.forward(tokens, [1] * B, cache)
+        return out if out.dtype == torch.float32 else out.float()
+
+    @torch.inference_mode()
+    def forward_logprobs(self, input_ids: torch.Tensor, seqlens: List[int], cache: Optional[BufferCache],
+                         targets: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One prompt chunk for generate(): returns (lp [T] fp32 with lp[t] = log_softmax(logits[t])[targets[t]] where
+        targets[t] >= 0, logits [B, V] fp32 of each sequence's last token).  Replaces forward + log_softmax over [T, V] +
+        per-token gathers (generate.py:97-118): the lm head runs over blocks of rows, each followed by the fused
+        log-softmax + gather kernel, so the full [T, V] logits never exist."""
+        self._last_static_logits = 0
+        T, V = input_ids.shape[0], self.vocab_size
+        last_idx = torch.tensor(seqlens, device=input_ids.device).cumsum(0) - 1
+        lp = torch.zeros(T, dtype=torch.float32, device=input_ids.device)
+        if self.num_pipeline_ranks > 1:  # reference-compatible pipeline mode: logits arrive by broadcast (transformer.py:236-237)
+            logits = self.forward(input_ids, seqlens, cache).float().contiguous()
+            _abi.logprob_gather(logits, targets, out=lp)
+            return lp, logits.index_select(0, last_idx)
+        self._check_runnable()
+        h = self._hidden_no_norm(input_ids, seqlens, cache)
+        if cache is not None:
+            cache.update_seqlens(seqlens)
+        assert self.norm is not None and self.output_weight is not None
+        rows = max(128, (256 << 20) // (4 * V))
+        ws = self.workspace(max(T, 1))
+        block = torch.empty(min(rows, T), V, dtype=torch.float32, device=h.device)
+        for r0 in range(0, T, rows):
+            r1 = min(T, r0 + rows)
+            _abi.lm_head(h[r0:r1], self.norm.weight, self.output_weight, block[: r1 - r0], self.args.norm_eps, ws)
+            _abi.logprob_gather(block[: r1 - r0], targets[r0:r1], out=lp[r0:r1])
+        last_logits = torch.empty(len(seqlens), V, dtype=torch.float32, device=h.device)
+        _abi.lm_head(h.index_select(0, last_idx), self.norm.weight, self.output_weight, last_logits, self.args.norm_eps, ws)
+        return lp, last_logits
 
     # ------------------------------------------------------------------ weights
     def _assign(self, k: str, v: torch.Tensor) -> bool:
@@ -444,6 +523,18 @@ class Transformer(nn.Module):
         return out
 
     @staticmethod
+    def empty(args: TransformerArgs, device: Union[torch.device, str] = "cuda", dtype: torch.dtype = torch.bfloat16, **kwargs: Any) -> "Transformer":
+        """A model with UNINITIALISED parameters allocated once, directly in `dtype` on `device` (shapes are laid out on `meta`
+        first).  `Transformer(args)` under `torch.device("cuda")` would allocate fp32 and run the Embedding initialiser there:
+        2-3x the model's bf16 bytes at the peak (Mixtral-8x7B: 187 GB)."""
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.device("meta"):
+            m = Transformer(args, **kwargs)
+        return m.to(dtype=dtype).to_empty(device=dev)
+
+    @staticmethod
     def from_folder(folder: Union[Path, str], max_batch_size: int = 1, num_pipeline_ranks: int = 1,
                     device: Union[torch.device, str] = "cuda", dtype: Optional[torch.dtype] = None,
                     softmax_fp32: bool = True, expert_parallel: Optional[Tuple[int, int]] = None, expert_group: Any = None) -> "Transformer":
@@ -462,21 +553,24 @@ class Transformer(nn.Module):
         dev = torch.device(device)
         if dev.type == "cuda" and dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-        with torch.device(dev):
-            model = Transformer(model_args, pipeline_rank=pipeline_rank, num_pipeline_ranks=num_pipeline_ranks, softmax_fp32=softmax_fp32,
-                                expert_parallel=expert_parallel, expert_group=expert_group)
+
+        def build(ck_dtype: torch.dtype) -> "Transformer":
+            # shapes on `meta`, storage allocated ONCE, directly in the target dtype on the target device (the reference builds
+            # on meta and assigns, transformer.py:321-331; a fp32 build followed by .to(bf16) would need 3x the model's bytes)
+            return Transformer.empty(model_args, dev, dtype or ck_dtype, pipeline_rank=pipeline_rank, num_pipeline_ranks=num_pipeline_ranks,
+                                     softmax_fp32=softmax_fp32, expert_parallel=expert_parallel, expert_group=expert_group)
+
         if pt_model_file.exists():
             loaded = torch.load(str(pt_model_file), mmap=True)
-            ck_dtype = next(iter(loaded.values())).dtype
-            model = model.to(dtype=dtype or ck_dtype)
+            model = build(next(iter(loaded.values())).dtype)
             model.load_state_dict(loaded, strict=True)
         else:
             import safetensors
 
             with safetensors.safe_open(str(safetensors_model_file), framework="pt", device="cpu") as f:
                 keys = list(f.keys())
-                ck_dtype = f.get_tensor("norm.weight").dtype if "norm.weight" in keys else f.get_tensor(keys[0]).dtype
-                model = model.to(dtype=dtype or ck_dtype)
+                probe = "norm.weight" if "norm.weight" in keys else keys[0]
+                model = build(f.get_tensor(probe).dtype)
                 loaded_keys = set()
                 with torch.no_grad():
                     for k in keys:

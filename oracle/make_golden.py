@@ -83,9 +83,79 @@ def run_reference(case: dict, seed: int = 1) -> Dict[str, torch.Tensor]:
     return out
 
 
+# ---- BASELINE.json configs[0]: "Mistral-7B shape, random-init bf16, 1 layer, batch=1, 128-token prompt + 32 decode on CPU
+# (reference path, plumbing)".  The full logits would be 21 MB; the fixture keeps what pins the path: the greedy tokens, every
+# log-probability generate() returns, the top-64 (value, index) of each step's logits and the first 256 vocabulary columns of
+# the prompt's logits.  With random-init weights the two largest of 32000 bf16 logits are a few ulps apart on average (the gap
+# of the top two order statistics is ~8 ulps, exponentially distributed), so over 32 steps some pick is always a near-tie that
+# any two correct implementations may resolve differently.  The fixture therefore records the reference's top-1/top-2 margin of
+# every step (in bf16 ulps); a step is DECISIVE when the margin is >= 3 ulps.  Token ids must be identical at every decisive
+# step (teacher-forced), and the free-running generate() must reproduce the reference's ids up to the first non-decisive step.
+# Among the first few weight seeds the one with the longest decisive prefix is kept.
+CONFIG1 = dict(shape="mistral-7b", over={"n_layers": 1}, dtype="bfloat16", prompt_lens=[128], max_tokens=32, max_batch=1, chunk=None)
+MIN_MARGIN_ULPS = 3
+TOPK = 64
+
+
+def bf16_ulp(x: torch.Tensor) -> torch.Tensor:
+    """Spacing of bf16 numbers at |x| (8 significand bits)."""
+    return torch.pow(2.0, torch.floor(torch.log2(x.abs().clamp_min(1e-30))) - 7)
+
+
+def run_config1(max_seeds: int = 6):
+    ref = ref_shims.import_reference()
+    case = CONFIG1
+    dtype = torch.bfloat16
+    best = None
+    for seed in range(1, max_seeds + 1):
+        p, prompts = case_inputs(case, seed)
+        args = ref.args.TransformerArgs.from_dict(dict(p))
+        args.max_batch_size = case["max_batch"]
+        with torch.device("meta"):
+            model = ref.transformer.Transformer(args)
+        model.load_state_dict(synth.synth_state_dict(p, seed, dtype), assign=True, strict=True)
+        model = model.to(device="cpu", dtype=dtype).eval()
+        recorded: List[torch.Tensor] = []
+        orig_forward = model.forward
+
+        def recording_forward(*a, **kw):
+            out = orig_forward(*a, **kw)
+            recorded.append(out.clone())
+            return out
+
+        model.forward = recording_forward
+        toks, logprobs = ref.generate.generate(prompts, model, max_tokens=case["max_tokens"], temperature=0.0)
+        # logits each of the 32 picks was made from: last prefill row, then the decode steps (the final forward is never sampled)
+        picked_from = torch.cat([recorded[0][-1:]] + [r for r in recorded[1:-1]], 0)  # [32, V]
+        top = picked_from.topk(TOPK, dim=-1)
+        margins = (top.values[:, 0] - top.values[:, 1]) / bf16_ulp(top.values[:, 0])
+        weak = (margins < MIN_MARGIN_ULPS).nonzero().flatten().tolist()
+        prefix = weak[0] if weak else case["max_tokens"]
+        print(f"config1 seed {seed}: decisive prefix {prefix}/32 steps, {32 - len(weak)} decisive steps, min margin {margins.min().item():.1f} ulps", flush=True)
+        if best is None or prefix > best[0]:
+            out = {"tokens": torch.tensor(toks, dtype=torch.int64), "logprobs": torch.tensor(sum(logprobs, []), dtype=torch.float64),
+                   "topk_values": top.values.contiguous(), "topk_indices": top.indices.contiguous(), "margin_ulps": margins.contiguous(),
+                   "prefill_logits_head": recorded[0][:, :256].contiguous()}  # first 256 vocab columns of all 128 prompt rows
+            best = (prefix, seed, out)
+        del model
+        if prefix == case["max_tokens"]:
+            break
+    return best[1], best[0], best[2]
+
+
 def main() -> None:
     GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
     import safetensors.torch
+
+    if "--config1" in sys.argv or "--all" in sys.argv:
+        seed, prefix, out = run_config1()
+        meta = {"case": json.dumps(CONFIG1), "seed": str(seed), "decisive_prefix": str(prefix), "min_margin_ulps": str(MIN_MARGIN_ULPS), "torch": torch.__version__,
+                "cpu_capability": torch.backends.cpu.get_cpu_capability(),
+                "reference": "mistralai/mistral-inference@2557e12 (v1.6.0) modules, unmodified, via oracle/ref_shims.py"}
+        safetensors.torch.save_file(out, str(GOLDEN_DIR / "config1_7b_1layer.safetensors"), metadata=meta)
+        print(f"config1_7b_1layer: seed={seed} tokens={out['tokens'].tolist()}")
+        if "--config1" in sys.argv:
+            return
 
     for name, case in CASES.items():
         out = run_reference(case)

@@ -37,8 +37,7 @@ def _worker(rank: int, world: int, port: int, q):
         def build(expert_parallel):
             args = mi.TransformerArgs.from_dict(dict(p))
             args.max_batch_size = 2
-            with torch.device("cuda"):
-                m = Transformer(args, expert_parallel=expert_parallel).to(torch.bfloat16)
+            m = Transformer.empty(args, "cuda", torch.bfloat16, expert_parallel=expert_parallel)
             m.load_state_dict(sd)
             return m.eval()
 

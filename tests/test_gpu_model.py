@@ -1,14 +1,18 @@
 """GPU parity of the whole path through the public API (Transformer.forward / generate), against
-  (a) the committed outputs of the reference (tests/golden/), teacher-forced;
-  (b) the oracle restatement run on this machine's CPU on the same weights;
+  (a) the committed outputs of the reference (tests/golden/), teacher-forced, incl. BASELINE.json configs[0] token-id exact;
+  (b) the oracle restatement run on this machine's CPU on the same weights -- also at the REAL layer shapes of every
+      BASELINE config (2-layer slices of Mistral-7B, Nemo-12B, Mixtral-8x7B, Mixtral-8x22B);
   (c) the reference's own consistency property decode == (chunked) re-prefill (tests/test_generate.py:36-69,199-230).
 
-Tolerance: logits are bf16 values (stored as fp32) of magnitude <= ~2.4 here, i.e. 1 ulp = 2^-7..2^-6.  After L
-layers of bf16 roundings the CUDA path and the CPU oracle differ by a few ulps on a few logits: LOGIT_ATOL below.
-The north-star's "rtol 1e-3 / atol 1e-5" is tighter than one bf16 ulp (2^-8 relative) and therefore not
-attainable element-wise between ANY two correct bf16 implementations with different summation order (the oracle on
-another CPU does not meet it against itself: tests/test_oracle_golden.py); measured deltas are printed.
-Greedy token ids must match wherever the reference's own top-2 margin exceeds the tolerance.
+Tolerance (tests/util.py): logits are bf16 values (stored as fp32); two correct implementations that accumulate in a different
+order differ by ONE bf16 ulp on some of them, occasionally two after L layers of roundings: every logit must be within 2 bf16
+ulps at the scale of the largest logit (`logit_tol`), log-probabilities within 0.03.  The north-star's "rtol 1e-3 / atol 1e-5"
+is tighter than one bf16 ulp (2^-8 relative) and not attainable element-wise between ANY two correct bf16 implementations (the
+oracle on another CPU does not meet it against itself: tests/test_oracle_golden.py); measured deltas are printed.
+Greedy token ids must match wherever the reference's own top-2 margin exceeds that tolerance (both sides may move by it).
+MoE: top-k routing is discontinuous.  A token whose k-th / (k+1)-th router logits are within 2 ulps may legitimately be routed
+differently; `RouterProbe` finds those tokens in the oracle run, and ONLY rows of sequences that have seen such a token are
+exempt from the logit bound (their K/V differ from then on) -- every other row is held to the dense tolerance.
 """
 import pytest
 import torch
@@ -19,20 +23,30 @@ from mistral_inference_b200.cache import BufferCache
 from mistral_inference_b200.transformer import Transformer
 from oracle import restatement as R
 
-from .util import GOLDEN_CASES, case_params_prompts, load_golden, oracle_model
+from .util import (GOLDEN_CASES, LOGPROB_TOL, RouterProbe, case_params_prompts, load_golden, logit_tol, oracle_args, oracle_model)
 
 pytestmark = pytest.mark.gpu
-LOGIT_ATOL = 0.06
 BF16_CASES = [c for c in GOLDEN_CASES if not c.endswith("fp32")]
+RISKY_ULPS = 2.0
 
 
 def gpu_model(p: dict, max_batch: int, seed: int = 1) -> Transformer:
     args = mi.TransformerArgs.from_dict(dict(p))
     args.max_batch_size = max_batch
-    with torch.device("cuda"):
-        m = Transformer(args).to(torch.bfloat16)
+    m = Transformer.empty(args, "cuda", torch.bfloat16)
     m.load_state_dict(synth.synth_state_dict(p, seed, torch.bfloat16, "cuda"))
     return m.eval()
+
+
+def gpu_and_oracle(p: dict, max_batch: int, seed: int = 1):
+    """Same weights on both sides: generated once on the GPU (synth is bit-identical on CPU and GPU), copied to the host."""
+    args = mi.TransformerArgs.from_dict(dict(p))
+    args.max_batch_size = max_batch
+    m = Transformer.empty(args, "cuda", torch.bfloat16)
+    sd = synth.synth_state_dict(p, seed, torch.bfloat16, "cuda")
+    m.load_state_dict(sd)
+    om = R.OracleTransformer(oracle_args(p, max_batch), {k: v.cpu() for k, v in sd.items()})
+    return m.eval(), om
 
 
 def new_cache(m: Transformer, max_seq: int) -> BufferCache:
@@ -48,48 +62,131 @@ def new_cache(m: Transformer, max_seq: int) -> BufferCache:
 
 def report(tag, got, want):
     d = (got.float().cpu() - want.float().cpu()).abs()
-    print(f"\n[parity] {tag}: max|d|={d.max():.4f} mean|d|={d.mean():.5f} exact={(d == 0).float().mean():.3f}")
+    print(f"\n[parity] {tag}: max|d|={d.max():.4f} (tol {logit_tol(want):.4f}) mean|d|={d.mean():.5f} exact={(d == 0).float().mean():.3f}")
     return d
 
 
-def check_logits(d: torch.Tensor, moe: bool) -> None:
-    """Dense: every logit within LOGIT_ATOL.  MoE: top-k routing is discontinuous -- when two router logits are
-    within a bf16 ulp the CUDA path and the oracle may legitimately pick different experts for a token, which moves
-    that token's logits by more than rounding noise; tolerate a few such rows, bound everything else."""
-    if not moe:
-        assert d.max() <= LOGIT_ATOL, d.max()
-        return
-    bad_rows = (d.max(dim=-1).values > LOGIT_ATOL)
-    assert bad_rows.float().mean() <= 0.2, f"{int(bad_rows.sum())}/{bad_rows.numel()} rows beyond tolerance"
-    assert d[~bad_rows].max() <= LOGIT_ATOL and d.mean() <= 0.01
+def check_rows(d: torch.Tensor, want: torch.Tensor, exempt: torch.Tensor = None, what: str = "") -> None:
+    """Every logit row within 2 bf16 ulps at logit scale, except rows flagged in `exempt` (MoE rows downstream of a router near-tie)."""
+    tol = logit_tol(want)
+    row_max = d.max(dim=-1).values
+    bad = row_max > tol
+    if exempt is not None:
+        unexplained = bad & ~exempt
+        assert not unexplained.any(), f"{what}: rows {unexplained.nonzero().flatten().tolist()} differ by {row_max[unexplained].max():.4f} > {tol:.4f} with no router near-tie upstream"
+        print(f"[parity] {what}: {int(bad.sum())} row(s) beyond tolerance, all downstream of a router near-tie; {int((~exempt).sum())}/{exempt.numel()} rows held to {tol:.4f}")
+    else:
+        assert not bad.any(), f"{what}: max|d| = {row_max.max():.4f} > {tol:.4f} (2 bf16 ulps at logit scale)"
+
+
+def row_seq(seqlens):
+    return torch.repeat_interleave(torch.arange(len(seqlens)), torch.tensor(seqlens))
+
+
+class Contamination:
+    """Per sequence: has a token with a router near-tie been seen (in the oracle run)?  Rows of such sequences are exempt from now on."""
+
+    def __init__(self, B: int, moe: bool):
+        self.flag = torch.zeros(B, dtype=torch.bool)
+        self.moe = moe
+
+    def rows(self, margins: torch.Tensor, seqlens) -> torch.Tensor:
+        """`margins` [T] of this forward -> exempt mask [T] (a prefill row is exempt if ANY earlier-or-same token of its sequence
+        in this chunk is risky: causal attention only looks back; conservatively the whole sequence's chunk is flagged)."""
+        if not self.moe:
+            return None
+        seq = row_seq(seqlens)
+        risky = margins <= RISKY_ULPS
+        for b in range(len(seqlens)):
+            if risky[seq == b].any():
+                self.flag[b] = True
+        return self.flag[seq]
 
 
 @pytest.mark.parametrize("name", BF16_CASES)
 def test_golden_teacher_forced(name):
     case, gold, _ = load_golden(name)
     p, prompts = case_params_prompts(case)
-    m = gpu_model(p, case["max_batch"])
-    B = len(prompts)
-    cache = new_cache(m, max(len(x) for x in prompts) + case["max_tokens"])
-    logits = m.forward(torch.tensor(sum(prompts, []), device="cuda"), [len(x) for x in prompts], cache)
     moe = p.get("moe") is not None
-    d = report(f"{name} prefill", logits, gold["prefill_logits"])
-    check_logits(d, moe)
-    toks = gold["tokens"]  # [B, max_tokens] the reference's greedy choices
-    agree = total = 0
-    for step in range(toks.shape[1]):
-        logits = m.forward(toks[:, step].to("cuda"), [1] * B, cache)
-        want = gold["decode_logits"][step]
-        d = report(f"{name} decode step {step}", logits, want)
-        check_logits(d, moe)
-        if step + 1 < toks.shape[1] and not moe:  # the next greedy token, wherever the reference's margin is decisive
-            top2 = want.topk(2, dim=-1).values
-            decisive = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_ATOL
-            pick = logits.argmax(-1).cpu()
-            assert torch.equal(pick[decisive], toks[:, step + 1][decisive])
-            agree += int((pick == toks[:, step + 1]).sum())
-            total += B
-    print(f"[parity] {name}: greedy token agreement with the reference {agree}/{total}")
+    m = gpu_model(p, case["max_batch"])
+    om = oracle_model(p, case["max_batch"]) if moe else None  # only to find router near-ties (the expected values are the reference's)
+    B = len(prompts)
+    seqlens = [len(x) for x in prompts]
+    cache = new_cache(m, max(seqlens) + case["max_tokens"])
+    ocache = om.new_cache(max(seqlens) + case["max_tokens"]) if moe else None
+    cont = Contamination(B, moe)
+    with RouterProbe() as probe:
+        flat = torch.tensor(sum(prompts, []))
+        logits = m.forward(flat.cuda(), seqlens, cache)
+        if moe:
+            om.forward(flat, seqlens, ocache)
+        d = report(f"{name} prefill", logits, gold["prefill_logits"])
+        check_rows(d, gold["prefill_logits"], cont.rows(probe.end_forward(), seqlens), f"{name} prefill")
+        toks = gold["tokens"]  # [B, max_tokens] the reference's greedy choices
+        agree = total = decisive_n = 0
+        for step in range(toks.shape[1]):
+            logits = m.forward(toks[:, step].to("cuda"), [1] * B, cache)
+            if moe:
+                om.forward(toks[:, step], [1] * B, ocache)
+            want = gold["decode_logits"][step]
+            d = report(f"{name} decode step {step}", logits, want)
+            exempt = cont.rows(probe.end_forward(), [1] * B)
+            check_rows(d, want, exempt, f"{name} decode step {step}")
+            if step + 1 < toks.shape[1]:  # the next greedy token, wherever the reference's margin is decisive
+                top2 = want.topk(2, dim=-1).values
+                decisive = (top2[:, 0] - top2[:, 1]) > 2 * logit_tol(want)
+                if exempt is not None:
+                    decisive &= ~exempt
+                pick = logits.argmax(-1).cpu()
+                assert torch.equal(pick[decisive], toks[:, step + 1][decisive])
+                agree += int((pick == toks[:, step + 1]).sum())
+                decisive_n += int(decisive.sum())
+                total += B
+    print(f"[parity] {name}: greedy token agreement with the reference {agree}/{total} ({decisive_n} with a decisive margin: all equal)")
+
+
+def test_config1_token_id_exact():
+    """BASELINE.json configs[0]: Mistral-7B shape, 1 layer, bf16, batch 1, 128-token prompt + 32 greedy tokens, against the
+    committed outputs of the reference's own generate() (oracle/make_golden.py --config1).  The fixture records the reference's
+    top-1/top-2 margin at every step; a step is decisive at >= 3 bf16 ulps (with random-init weights some of 32 picks among
+    32000 bf16 logits are always near-ties).  Teacher-forced: identical token ids at EVERY decisive step and the top-64 logits
+    within 2 ulps at every step.  Free-running generate(): identical ids up to the first non-decisive step."""
+    case, gold, meta = load_golden("config1_7b_1layer")
+    seed, prefix = int(meta["seed"]), int(meta["decisive_prefix"])
+    p = synth.shape(case["shape"], **case["over"])
+    prompts = [synth.synth_prompt(n, p["vocab_size"], seed * 100 + i) for i, n in enumerate(case["prompt_lens"])]
+    m = gpu_model(p, case["max_batch"], seed=seed)
+    ref_toks = gold["tokens"][0].tolist()
+    decisive = (gold["margin_ulps"] >= 3).tolist()
+    # ---- free-running, through the public generate()
+    toks, lp = mi.generate(prompts, m, max_tokens=case["max_tokens"], temperature=0.0)
+    assert toks[0][:prefix] == ref_toks[:prefix], "greedy token ids differ from the reference before its first near-tie"
+    same = 0
+    while same < 32 and toks[0][same] == ref_toks[same]:
+        same += 1
+    want_lp = gold["logprobs"].tolist()
+    n_cmp = 127 + same  # log-probabilities up to the first divergence are comparable
+    worst = max(abs(a - b) for a, b in zip(lp[0][:n_cmp], want_lp[:n_cmp]))
+    assert worst <= LOGPROB_TOL
+    # ---- teacher-forced on the reference's tokens: every decisive pick identical, top-64 logits within 2 ulps
+    cache = new_cache(m, 128 + 32)
+    logits = m.forward(torch.tensor(prompts[0], device="cuda"), [128], cache)
+    d = report("config1 prefill (vocab columns 0..255)", logits[:, :256], gold["prefill_logits_head"])
+    assert d.max() <= logit_tol(gold["prefill_logits_head"])
+    last = logits[-1:]
+    agree = 0
+    for step in range(32):
+        idx = gold["topk_indices"][step]
+        got = last[0].cpu()[idx]
+        dd = (got - gold["topk_values"][step]).abs().max().item()
+        assert dd <= logit_tol(gold["topk_values"][step]), (step, dd)
+        pick = int(last[0].argmax())
+        if decisive[step]:
+            assert pick == ref_toks[step], f"step {step}: decisive pick differs from the reference"
+        agree += pick == ref_toks[step]
+        last = m.forward(gold["tokens"][:, step].cuda(), [1], cache)
+    print(f"\n[parity] config1 (7B shape, 1 layer, 128+32): teacher-forced ids equal at {agree}/32 steps ({sum(decisive)} decisive: all equal); "
+          f"free-running generate() identical for the first {same} tokens (reference's first near-tie at step {prefix}); max|d logprob|={worst:.4f}")
 
 
 @pytest.mark.parametrize("shape,over,lens,chunk", [
@@ -97,28 +194,51 @@ def test_golden_teacher_forced(name):
     ("tiny", {"sliding_window": 5}, [11, 9, 10], 4),
     ("tiny", {"sliding_window": [4, None]}, [70, 68], 33),
     ("tiny-moe", {"sliding_window": 3}, [11, 12], 5),
+    ("tiny-moe", {}, [40, 37, 33, 35, 36], None),  # 5 sequences: batched MoE decode (grouped experts), 181-token MoE prefill
     ("ref-test", {}, [8, 4, 4, 4], None),  # the shape of the reference's own tests (tests/test_generate.py:40-50)
 ])
 def test_generate_vs_oracle_and_self_consistency(shape, over, lens, chunk):
     p = synth.shape(shape, **over)
     if shape == "ref-test":
         p["vocab_size"] = 4096  # keep the CPU oracle quick
+    moe = p.get("moe") is not None
     prompts = [synth.synth_prompt(n, p["vocab_size"], 60 + i) for i, n in enumerate(lens)]
     B, max_tokens = len(prompts), 6
     m = gpu_model(p, B + 1)  # max_batch_size > B exercises cache[:B] (tests/test_generate.py:212)
     om = oracle_model(p, B + 1)
     # (b) teacher-forced on the oracle's greedy tokens
     o_toks, o_lp, o_step = R.generate(prompts, om, max_tokens=max_tokens, chunk_size=chunk, return_logits=True)
-    cache = new_cache(m, max(lens) + max_tokens)
+    cache, ocache = new_cache(m, max(lens) + max_tokens), om.new_cache(max(lens) + max_tokens)
+    cont = Contamination(B, moe)
     last = None
-    for s in range(0, max(lens), chunk or max(lens)):
-        chunks = [pr[s:s + (chunk or max(lens))] for pr in prompts]
-        logits = m.forward(torch.tensor(sum(chunks, []), device="cuda"), [len(c) for c in chunks], cache)
-        last = logits[torch.tensor([len(c) for c in chunks]).cumsum(0) - 1]
-    for step in range(max_tokens):
-        d = report(f"{shape}{over} step {step}", last, o_step[step])
-        check_logits(d, p.get("moe") is not None)
-        last = m.forward(torch.tensor([t[step] for t in o_toks], device="cuda"), [1] * B, cache)
+    with RouterProbe() as probe:
+        for s in range(0, max(lens), chunk or max(lens)):
+            chunks = [pr[s:s + (chunk or max(lens))] for pr in prompts]
+            sl = [len(c) for c in chunks]
+            flat = torch.tensor(sum(chunks, []))
+            logits = m.forward(flat.cuda(), sl, cache)
+            want = om.forward(flat, sl, ocache)
+            d = report(f"{shape}{over} prefill chunk @{s}", logits, want)
+            check_rows(d, want, cont.rows(probe.end_forward(), sl), f"{shape}{over} prefill chunk @{s}")
+            last = logits[torch.tensor(sl).cumsum(0) - 1]
+        agree = n_dec = 0
+        for step in range(max_tokens):
+            d = report(f"{shape}{over} step {step}", last, o_step[step])
+            exempt = cont.flag.clone() if moe else None
+            check_rows(d, o_step[step], exempt, f"{shape}{over} step {step}")
+            top2 = o_step[step].topk(2, dim=-1).values
+            decisive = (top2[:, 0] - top2[:, 1]) > 2 * logit_tol(o_step[step])
+            if exempt is not None:
+                decisive &= ~exempt
+            pick = last.argmax(-1).cpu()
+            assert torch.equal(pick[decisive], torch.tensor([t[step] for t in o_toks])[decisive])
+            agree += int(decisive.sum())
+            n_dec += B
+            nxt = torch.tensor([t[step] for t in o_toks])
+            last = m.forward(nxt.cuda(), [1] * B, cache)
+            om.forward(nxt, [1] * B, ocache)
+            cont.rows(probe.end_forward(), [1] * B)
+    print(f"[parity] {shape}{over}: greedy token ids equal to the oracle's at all {agree} decisive picks (of {n_dec})")
     # (c) the reference's property through the public generate(): decode == chunked re-prefill
     toks, lp = mi.generate(prompts, m, max_tokens=max_tokens, temperature=0.0)
     assert len(toks) == B and all(len(t) == max_tokens for t in toks)
@@ -132,15 +252,19 @@ def test_generate_vs_oracle_and_self_consistency(shape, over, lens, chunk):
     worst = max(abs(a - b) for x, y in zip(lp, lp2) for a, b in zip(x, y))
     print(f"[parity] {shape}{over}: decode vs re-prefill logprob max|d|={worst:.4f}")
     assert all(len(x) == len(y) for x, y in zip(lp, lp2))
-    assert worst < 0.12  # bf16; the reference's 5e-4 is its fp32 bound
+    if not moe:  # (a router near-tie between the two runs of the SAME kernels cannot be ruled out for MoE: bounded loosely there)
+        assert worst <= LOGPROB_TOL  # bf16; the reference's 5e-4 is its fp32 bound
+    else:
+        assert worst < 0.12
 
 
 def test_forward_without_cache():
     p = synth.shape("tiny")
     m, om = gpu_model(p, 2), oracle_model(p, 2)
     toks = torch.tensor(synth.synth_prompt(13, p["vocab_size"], 5))
-    d = report("no-cache forward", m.forward(toks.cuda(), [6, 7]), om.forward(toks, [6, 7]))
-    assert d.max() <= LOGIT_ATOL
+    want = om.forward(toks, [6, 7])
+    d = report("no-cache forward", m.forward(toks.cuda(), [6, 7]), want)
+    assert d.max() <= logit_tol(want)
 
 
 @pytest.mark.parametrize("over,lens", [
@@ -155,11 +279,13 @@ def test_long_first_prefill_vs_oracle(over, lens):
     m, om = gpu_model(p, len(lens)), oracle_model(p, len(lens))
     toks = torch.tensor(synth.synth_prompt(sum(lens), p["vocab_size"], 11))
     cache, ocache = new_cache(m, max(lens) + 8), om.new_cache(max(lens) + 8)
-    d = report(f"long first prefill {over} {lens}", m.forward(toks.cuda(), lens, cache), om.forward(toks, lens, ocache))
-    assert d.max() <= LOGIT_ATOL and d.mean() <= 0.004
+    want = om.forward(toks, lens, ocache)
+    d = report(f"long first prefill {over} {lens}", m.forward(toks.cuda(), lens, cache), want)
+    assert d.max() <= logit_tol(want) and d.mean() <= 0.004
     nxt = torch.tensor([3 + b for b in range(len(lens))])
-    d = report(f"decode after long prefill {over} {lens}", m.forward(nxt.cuda(), [1] * len(lens), cache), om.forward(nxt, [1] * len(lens), ocache))
-    assert d.max() <= LOGIT_ATOL
+    want = om.forward(nxt, [1] * len(lens), ocache)
+    d = report(f"decode after long prefill {over} {lens}", m.forward(nxt.cuda(), [1] * len(lens), cache), want)
+    assert d.max() <= logit_tol(want)
 
 
 def test_sampling_path_runs():
@@ -168,6 +294,31 @@ def test_sampling_path_runs():
     torch.manual_seed(0)
     toks, lp = mi.generate([[1, 2, 3], [4, 5, 6, 7]], m, max_tokens=5, temperature=0.7, eos_id=None)
     assert len(toks) == 2 and all(len(t) == 5 for t in toks) and all(0 <= x < p["vocab_size"] for t in toks for x in t)
+    assert all(len(x) == n - 1 + 5 for x, n in zip(lp, (3, 4))) and all(v <= 0 for x in lp for v in x)
+
+
+def test_generate_eos_and_zero_tokens():
+    """generate.py:128-132,142-146: stop at the first step at which every sequence has emitted eos (that step is dropped); [] for max_tokens == 0."""
+    p = synth.shape("tiny")
+    m = gpu_model(p, 2)
+    prompts = [[1, 2, 3], [4, 5, 6, 7]]
+    toks, lp = mi.generate(prompts, m, max_tokens=40, temperature=0.0)
+    # pick as eos the token sequence 0 emits at step 5; sequence 1 must then emit it later for the loop to stop -- use its own
+    # step-9 token if equal, otherwise just check the no-early-stop path plus the forced early stop below
+    eos = toks[0][5]
+    steps = [min([s for s, t in enumerate(seq) if t == eos] or [10 ** 9]) for seq in toks]
+    expect = max(steps) if max(steps) < 10 ** 9 else 40
+    toks2, lp2 = mi.generate(prompts, m, max_tokens=40, temperature=0.0, eos_id=eos)
+    assert len(toks2[0]) == expect and [t[:expect] for t in toks] == toks2
+    assert all(len(x) == len(pr) - 1 + expect for x, pr in zip(lp2, prompts))
+    # single sequence: stops right at its first eos, which is not returned
+    t1, _ = mi.generate([prompts[0]], m, max_tokens=40, temperature=0.0)
+    e1 = t1[0][7]
+    first = t1[0].index(e1)
+    t2, l2 = mi.generate([prompts[0]], m, max_tokens=40, temperature=0.0, eos_id=e1)
+    assert t2 == [t1[0][:first]] if first > 0 else t2 == []
+    t0, l0 = mi.generate(prompts, m, max_tokens=0, temperature=0.0)
+    assert t0 == [] and [len(x) for x in l0] == [2, 3]
 
 
 def test_full_size_7b_layer_properties():
@@ -180,24 +331,30 @@ def test_full_size_7b_layer_properties():
     gen2, lp2 = mi.generate([prompt + toks[0]], m, max_tokens=0, temperature=0.0, chunk_size=170)
     worst = max(abs(a - b) for a, b in zip(lp[0], lp2[0]))
     print(f"[parity] 7B-shape 2-layer ring-wrap consistency: max|d logprob|={worst:.4f}")
-    assert worst < 0.12
+    assert worst <= LOGPROB_TOL
+
+
+REAL_SHAPES = [
+    ("mistral-7b", {"n_layers": 2, "vocab_size": 4096, "sliding_window": 64}, 100, 6),  # real layer shapes (K chunks of 3584); ring wraps
+    ("mistral-nemo-12b", {"n_layers": 2, "vocab_size": 4096}, 140, 4),  # BASELINE config 3 shape: dim 5120 != H*hd, no window
+    ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 40, 4),       # real expert shapes: 2 x (8 experts x 176 M params)
+    ("mixtral-8x22b", {"n_layers": 2, "vocab_size": 4096}, 40, 3),      # BASELINE config 5 shape: H/KV = 6, dim 6144, hidden 16384
+]
 
 
 @pytest.mark.parametrize("shape,over,prompt_len,steps", [
     ("tiny", {}, 9, 12),
     ("tiny", {"sliding_window": 6}, 9, 12),                 # ring wraps
     ("tiny", {"sliding_window": [5, None]}, 20, 8),
-    ("mistral-7b", {"n_layers": 2, "vocab_size": 4096, "sliding_window": 64}, 100, 6),  # real layer shapes (K chunks of 3584)
     ("tiny-moe", {}, 9, 10),                                  # in-kernel router + experts (moe.py:24-32)
     ("tiny-moe", {"sliding_window": 5}, 12, 8),
-    ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 40, 4),  # real expert shapes: 2 x (8 experts x 176 M params)
-    ("mistral-nemo-12b", {"n_layers": 2, "vocab_size": 4096}, 140, 4),  # BASELINE config 3 shape: dim 5120 != H*hd, no window
-    ("mixtral-8x22b", {"n_layers": 2, "vocab_size": 4096}, 40, 3),      # BASELINE config 5 shape: H/KV = 6, dim 6144, hidden 16384
-])
+] + REAL_SHAPES)
 def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
-    """The persistent one-kernel-per-token decode step against (a) the per-op kernel path and (b) the CPU oracle."""
+    """The persistent one-kernel-per-token decode step against (a) the CPU oracle -- at the tiny shapes AND at the real layer shapes
+    of every BASELINE config -- and (b) the per-op kernel path, which is held to the same oracle."""
     p = synth.shape(shape, **over)
-    m = gpu_model(p, 1)
+    moe = p.get("moe") is not None
+    m, om = gpu_and_oracle(p, 1)
     prompt = synth.synth_prompt(prompt_len, p["vocab_size"], 21)
     toks = synth.synth_prompt(steps, p["vocab_size"], 22)  # teacher-forced continuation
 
@@ -213,18 +370,57 @@ def test_decode_megakernel(shape, over, prompt_len, steps, monkeypatch):
     # fused greedy argmax of the last step == torch.argmax of the logits it produced (first index on ties)
     assert int(m.last_argmax.item()) == int(mk[-1].argmax().item())
     per_op, c2 = run(False)
-    moe = p.get("moe") is not None
+    # the oracle on the same weights, and which tokens sit on a router near-tie
+    with RouterProbe() as probe:
+        oc = om.new_cache(prompt_len + steps + 1)
+        om.forward(torch.tensor(prompt), [prompt_len], oc)
+        risky = bool((probe.end_forward() <= RISKY_ULPS).any()) if moe else False
+        want, exempt = [], []
+        for t in toks:
+            want.append(om.forward(torch.tensor([t]), [1], oc))
+            risky = risky or (moe and bool((probe.end_forward() <= RISKY_ULPS).any()))
+            exempt.append(risky)
+    want = torch.cat(want, 0)
+    exempt = torch.tensor(exempt) if moe else None
+    d = report(f"megakernel vs oracle {shape}{over}", mk, want)
+    check_rows(d, want, exempt, f"megakernel vs oracle {shape}{over}")
+    d = report(f"per-op path vs oracle {shape}{over}", per_op, want)
+    check_rows(d, want, exempt, f"per-op vs oracle {shape}{over}")
     d = report(f"megakernel vs per-op {shape}{over}", mk, per_op)
-    check_logits(d, moe)
-    for i in ([] if moe else c1.cache_k):  # (an expert flip changes later layers' K/V legitimately: dense models only)  # the rings written by both paths agree (1 bf16 ulp on a few elements)
+    check_rows(d, want, exempt, f"megakernel vs per-op {shape}{over}")
+    for i in ([] if moe else c1.cache_k):  # the rings written by both paths agree (1 bf16 ulp on a few elements); dense models only
         a, b = c1.cache_k[i][0].float(), c2.cache_k[i][0].float()
         ok = torch.isfinite(b)
         assert torch.equal(torch.isfinite(a), ok)
-        assert (a[ok] - b[ok]).abs().max() <= 0.07
-    if shape.startswith("tiny"):
-        om = oracle_model(p, 1)
-        oc = om.new_cache(prompt_len + steps + 1)
-        om.forward(torch.tensor(prompt), [prompt_len], oc)
-        want = torch.cat([om.forward(torch.tensor([t]), [1], oc) for t in toks], 0)
-        d = report(f"megakernel vs oracle {shape}{over}", mk, want)
-        check_logits(d, moe)
+        assert (a[ok] - b[ok]).abs().max() <= 2 * 2.0 ** -7 * max(1.0, b[ok].abs().max().item())
+
+
+@pytest.mark.parametrize("shape,over,B,prompt_len,steps", [
+    ("mistral-nemo-12b", {"n_layers": 2, "vocab_size": 4096}, 8, 48, 3),   # BASELINE config 3 layer shape, batched decode
+    ("mistral-7b", {"n_layers": 2, "vocab_size": 4096, "sliding_window": 64}, 32, 70, 3),  # B = 32, ring wraps
+    ("mixtral-8x7b", {"n_layers": 2, "vocab_size": 4096}, 8, 40, 3),       # BASELINE config 4: B = 8 MoE decode (grouped experts)
+    ("mixtral-8x22b", {"n_layers": 1, "vocab_size": 4096}, 16, 24, 2),     # BASELINE config 5: B = 16
+])
+def test_batched_decode_real_shapes_vs_oracle(shape, over, B, prompt_len, steps):
+    """Batched decode (B = 8..32: the small-batch weight-streaming tcgen05 GEMMs, split-KV decode attention, device-side step
+    state, grouped MoE) at the real layer shapes of BASELINE configs 3-5 against the CPU oracle, CUDA-graph replay included."""
+    p = synth.shape(shape, **over)
+    moe = p.get("moe") is not None
+    m, om = gpu_and_oracle(p, B)
+    prompts = [synth.synth_prompt(prompt_len - (b % 3), p["vocab_size"], 300 + b) for b in range(B)]
+    seqlens = [len(x) for x in prompts]
+    cache, ocache = new_cache(m, prompt_len + steps + 2), om.new_cache(prompt_len + steps + 2)
+    cont = Contamination(B, moe)
+    with RouterProbe() as probe:
+        flat = torch.tensor(sum(prompts, []))
+        got = m.forward(flat.cuda(), seqlens, cache)
+        want = om.forward(flat, seqlens, ocache)
+        d = report(f"{shape} B={B} prefill", got, want)
+        check_rows(d, want, cont.rows(probe.end_forward(), seqlens), f"{shape} B={B} prefill")
+        nxt = want[torch.tensor(seqlens).cumsum(0) - 1].argmax(-1)
+        for step in range(steps + 2):  # >= 3 steps: eager warm-up, graph capture, graph replay
+            got = m.forward(nxt.cuda(), [1] * B, cache)
+            want = om.forward(nxt, [1] * B, ocache)
+            d = report(f"{shape} B={B} decode step {step}", got, want)
+            check_rows(d, want, cont.rows(probe.end_forward(), [1] * B), f"{shape} B={B} decode step {step}")
+            nxt = want.argmax(-1)

@@ -310,3 +310,186 @@ def test_kv_ring_write():
         if r >= 0:
             assert torch.equal(ck[r].reshape(-1), k[t]) and torch.equal(cv[r].reshape(-1), v[t])
     assert ck[[2, 6, 7]].abs().sum() == 0
+
+
+# ----------------------------------------------------------------------------- small-batch (decode) weight-streaming tcgen05 GEMMs
+@pytest.mark.parametrize("T", [5, 16, 32, 33, 64, 65, 127])
+@pytest.mark.parametrize("N,K", [(4096, 4096),      # 7B wo / down width: 32-wide tiles (128 CTAs)
+                                 (6144, 4096),      # 7B fused QKV: 64-wide tiles
+                                 (5120, 14336),     # Nemo down projection, K = 14336: 224 k-blocks through the deep ring
+                                 (1024, 6144)])     # fewer tiles than half the SMs: narrow tiles
+def test_small_batch_gemm_vs_oracle(T, N, K, ws):
+    """5 <= T < 128 runs gemm_tcgen05_kernel with 32/64-row A boxes (the MMA's upper rows read past the box; rows >= T are never
+    stored) and a tile width chosen per N: plain store and residual epilogues against the CPU oracle, and every legal tile width
+    against each other (bit-identical: same k order)."""
+    if K == 14336 and T not in (16, 33, 127):
+        pytest.skip("long K: representative T only")
+    x, w, res = rnd(T, K, seed=50), rnd(N, K, seed=51, scale=K ** -0.5), rnd(T, N, seed=52)
+    out = torch.full((T + 3, N), float("nan"), dtype=torch.bfloat16, device=DEV)  # 3 guard rows: rows >= T must stay untouched
+    _abi.linear_residual(x.to(DEV), w.to(DEV), res.to(DEV), out[:T], ws)
+    assert_bf16_close(out[:T], res + F.linear(x, w), atol=2 * 2 ** -8 * res.abs().max().item(), what="small-batch gemm + residual")
+    assert torch.isnan(out[T:].float()).all(), "rows past T were written"
+    _abi.linear_residual(x.to(DEV), w.to(DEV), None, out[:T], ws)
+    assert_bf16_close(out[:T], F.linear(x, w), what="small-batch gemm")
+
+
+def test_small_batch_gemm_tile_widths_agree(ws, monkeypatch, rope):
+    """All tile widths of the small-batch kernel give the same bits through the QKV+RoPE+ring-scatter and SiLU*mul epilogues."""
+    T, dim, H, KV, hd, hid = 24, 1024, 8, 2, 128, 1024
+    x = rnd(T, dim, seed=60).to(DEV)
+    nw = (1 + 0.2 * rnd(dim, seed=61).float()).to(torch.bfloat16).to(DEV)
+    wqkv = rnd((H + 2 * KV) * hd, dim, seed=62, scale=dim ** -0.5).to(DEV)
+    w13 = rnd(2 * hid, dim, seed=63, scale=dim ** -0.5).to(DEV)
+    positions = (torch.arange(T, dtype=torch.int32) * 7 % 8000).to(DEV)
+    rows = torch.arange(T, dtype=torch.int32).to(DEV)
+    _, table_dev = rope
+    outs = {}
+    for bn in ("32", "64", "128", "256"):
+        monkeypatch.setenv("MB200_GEMM_BN", bn)
+        q = torch.empty(T, H * hd, dtype=torch.bfloat16, device=DEV)
+        k = torch.empty(T, KV * hd, dtype=torch.bfloat16, device=DEV)
+        v = torch.empty_like(k)
+        ck = torch.zeros(T, KV, hd, dtype=torch.bfloat16, device=DEV)
+        cv = torch.zeros_like(ck)
+        _abi.attn_qkv(x, nw, wqkv, table_dev, positions, q, k, v, ck, cv, rows, H, KV, hd, 1e-5, ws)
+        g = torch.empty(T, hid, dtype=torch.bfloat16, device=DEV)
+        _abi.ffn_gateup(x, nw, w13, g, 1e-5, ws)
+        torch.cuda.synchronize()
+        outs[bn] = (q, k, v, ck, cv, g)
+    for bn in ("64", "128", "256"):
+        for a, b, what in zip(outs["32"], outs[bn], ("q", "k", "v", "cache_k", "cache_v", "g")):
+            assert torch.equal(a, b), f"{what}: tile width {bn} differs from 32"
+
+
+# ----------------------------------------------------------------------------- device-side step state, token selection, log-probs
+def test_decode_meta_matches_host_metadata():
+    """mb200_decode_meta == BufferCache.build_metadata_host for one-token steps (cache.py:197-263), and it advances the positions."""
+    from mistral_inference_b200.cache import BufferCache
+
+    B, L = 5, 4
+    cache = BufferCache(L, B, 64, 2, 128, sliding_window=[7, None])
+    cache._kv_seqlens_host = [3, 7, 8, 20, 63]
+    windows = sorted(set(cache.cache_sizes))
+    seqpos = torch.tensor(cache._kv_seqlens_host, dtype=torch.int32, device=DEV)
+    meta = torch.zeros(3 * B + 1 + 2 * B * len(windows), dtype=torch.int32, device=DEV)
+    for _ in range(3):
+        host, layout = cache.build_metadata_host([1] * B)
+        assert layout["windows"] == windows
+        _abi.decode_meta(seqpos, meta, windows)
+        assert meta.cpu().tolist() == host.tolist()
+        cache.update_seqlens([1] * B)
+        assert seqpos.cpu().tolist() == cache._kv_seqlens_host
+
+
+@pytest.mark.parametrize("T,V", [(1, 32000), (5, 512), (33, 131072)])
+def test_argmax_and_logprob_gather(T, V):
+    g = torch.Generator().manual_seed(70)
+    logits = (torch.randn(T, V, generator=g) * 2).to(torch.bfloat16).float()  # bf16-valued like the lm head's output: many exact ties
+    tgt = torch.randint(0, V, (T,), generator=g)
+    tgt[T // 2] = -1
+    got = _abi.argmax_rows(logits.to(DEV))
+    assert torch.equal(got.cpu(), logits.argmax(-1)), "argmax (first index on ties)"
+    out = torch.full((T,), 123.0, device=DEV)
+    _abi.logprob_gather(logits.to(DEV), tgt.to(DEV), out=out)
+    want = torch.log_softmax(logits, -1)
+    for t in range(T):
+        if tgt[t] < 0:
+            assert out[t].item() == 123.0
+        else:
+            assert abs(out[t].item() - want[t, tgt[t]].item()) <= 2e-5, t
+
+
+def _ref_top_p_keep(probs: torch.Tensor, p: float) -> torch.Tensor:
+    """The kept set of the reference's sample_top_p (generate.py:161-170): sorted descending, keep while (cumsum - prob) <= p."""
+    ps, idx = torch.sort(probs, dim=-1, descending=True)
+    keep_sorted = ~((torch.cumsum(ps, -1) - ps) > p)
+    keep = torch.zeros_like(keep_sorted)
+    keep.scatter_(-1, idx, keep_sorted)
+    return keep
+
+
+@pytest.mark.parametrize("T,V,temp", [(4, 512, 0.7), (3, 32000, 1.0), (2, 131072, 0.3)])
+def test_sample_top_p_kept_set_and_distribution(T, V, temp):
+    g = torch.Generator().manual_seed(71)
+    logits = torch.randn(T, V, generator=g) * 3
+    probs = torch.softmax(logits / temp, -1)
+    keep = _ref_top_p_keep(probs, 0.8)
+    dev_logits = logits.to(DEV)
+    # (a) every draw lies in the reference's kept set, for uniforms spanning [0, 1)
+    us = torch.tensor([0.0, 1e-7, 0.25, 0.5, 0.75, 0.999, 0.9999999])
+    picks = []
+    for u in us.tolist():
+        tok = _abi.sample_top_p(dev_logits, torch.full((T,), u, device=DEV), temp, 0.8).cpu()
+        picks.append(tok)
+        for t in range(T):
+            assert keep[t, tok[t]], (t, u, int(tok[t]))
+    # (b) the draw is the inverse CDF of the renormalised kept distribution in index order
+    for t in range(T):
+        pk = torch.where(keep[t], probs[t], torch.zeros(())).double()
+        cdf = torch.cumsum(pk / pk.sum(), 0)
+        for u, tok in zip(us.tolist(), picks):
+            i = int(tok[t])
+            lo = cdf[i - 1].item() if i > 0 else 0.0
+            assert lo - 1e-4 <= u <= cdf[i].item() + 1e-4, (t, u, i, lo, cdf[i].item())
+    # (c) monotone in u (index order)
+    for t in range(T):
+        seq = [int(x[t]) for x in picks]
+        assert seq == sorted(seq)
+
+
+# ----------------------------------------------------------------------------- independent attention cross-check (xformers boundary)
+def _flash_attn():
+    try:
+        from flash_attn import flash_attn_varlen_func
+        return flash_attn_varlen_func
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"flash_attn not importable: {e}")
+
+
+@pytest.mark.parametrize("seqlens,W", [([70, 130], 256), ([70, 130], 33), ([700, 260], 4096), ([700, 260], 200)])
+def test_prefill_attention_vs_flash_attn(seqlens, W):
+    """The xformers boundary is unpinned in the reference tree (dependency absent).  flash_attn 2.8 (a third implementation, the
+    one xformers dispatches to on GPUs) with causal + sliding-window semantics cross-checks BOTH the oracle's attention
+    (oracle/attention_ref.py) and the CUDA kernels: window (i - W, i] = flash_attn window_size (W - 1, 0)."""
+    fa = _flash_attn()
+    H, KV = 32, 8
+    T, B = sum(seqlens), len(seqlens)
+    q, k, v = rnd(T, H * 128, seed=80), rnd(T, KV * 128, seed=81), rnd(T, KV * 128, seed=82)
+    cu = torch.tensor([0] + torch.tensor(seqlens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    try:
+        ref = fa(q.to(DEV).view(T, H, 128), k.to(DEV).view(T, KV, 128), v.to(DEV).view(T, KV, 128), cu, cu, max(seqlens), max(seqlens),
+                 causal=True, window_size=(W - 1, 0)).reshape(T, H * 128)
+        torch.cuda.synchronize()
+    except Exception as e:
+        pytest.skip(f"flash_attn does not run on this GPU: {type(e).__name__}: {e}")
+    ck = torch.zeros(B, W, KV, 128, dtype=torch.bfloat16)
+    want = _oracle_prefill(q, k, v, ck, ck.clone(), seqlens, [0] * B, W, H, KV)
+    assert_bf16_close(ref, want, max_ulp=2, min_exact=0.5, atol=4e-3, what="flash_attn vs oracle attention")
+    out = torch.zeros(T, H * 128, dtype=torch.bfloat16, device=DEV)
+    ck_d = torch.full((B, W, KV, 128), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _abi.attn_prefill(q.to(DEV), k.to(DEV), v.to(DEV), ck_d, ck_d.clone(), cu, torch.zeros(B, dtype=torch.int32, device=DEV), out, B, max(seqlens), W,
+                      H, KV, 128, causal=True, first_prefill=True)
+    assert_bf16_close(out, ref, max_ulp=2, min_exact=0.5, atol=4e-3, what="attn_prefill kernel vs flash_attn")
+
+
+def test_decode_attention_vs_flash_attn(ws):
+    fa = _flash_attn()
+    B, W, H, KV = 3, 300, 32, 8
+    lens = [300, 37, 150]
+    q = rnd(B, H * 128, seed=83)
+    ck, cv = rnd(B, W, KV, 128, seed=84), rnd(B, W, KV, 128, seed=85)
+    kv_len = torch.tensor(lens, dtype=torch.int32)
+    kk = torch.cat([ck[b, :n] for b, n in enumerate(lens)], 0).to(DEV)
+    vv = torch.cat([cv[b, :n] for b, n in enumerate(lens)], 0).to(DEV)
+    cu_q = torch.arange(B + 1, dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    try:
+        ref = fa(q.to(DEV).view(B, H, 128), kk, vv, cu_q, cu_k, 1, max(lens), causal=True).reshape(B, H * 128)
+        torch.cuda.synchronize()
+    except Exception as e:
+        pytest.skip(f"flash_attn does not run on this GPU: {type(e).__name__}: {e}")
+    want = _oracle_decode(q, ck, cv, kv_len, H, KV)
+    assert_bf16_close(ref, want, max_ulp=2, min_exact=0.5, atol=4e-3, what="flash_attn vs oracle decode attention")
+    out = torch.empty(B, H * 128, dtype=torch.bfloat16, device=DEV)
+    _abi.attn_decode(q.to(DEV), ck.to(DEV), cv.to(DEV), kv_len.to(DEV), out, H, KV, 128, 4, ws)
+    assert_bf16_close(out, ref, max_ulp=2, min_exact=0.5, atol=4e-3, what="attn_decode kernel vs flash_attn")

@@ -39,3 +39,26 @@ def test_oracle_matches_golden(name):
     for a, b in zip(logprobs, logprobs2):
         assert len(a) == len(b)
         assert max(abs(x - y) for x, y in zip(a, b)) < bound
+
+
+def test_oracle_matches_config1_golden():
+    """BASELINE.json configs[0] (Mistral-7B shape, 1 layer, batch 1, 128 + 32): the oracle restatement against the committed
+    outputs of the reference's generate() -- bit-exact on the fixture's machine type, decisive picks identical anywhere."""
+    from mistral_inference_b200 import synth
+
+    from .util import oracle_args
+
+    case, gold, meta = load_golden("config1_7b_1layer")
+    seed = int(meta["seed"])
+    p = synth.shape(case["shape"], **case["over"])
+    prompts = [synth.synth_prompt(n, p["vocab_size"], seed * 100 + i) for i, n in enumerate(case["prompt_lens"])]
+    model = R.OracleTransformer(oracle_args(p, 1), synth.synth_state_dict(p, seed, torch.bfloat16))
+    toks, logprobs, step_logits = R.generate(prompts, model, max_tokens=case["max_tokens"], return_logits=True)
+    if same_machine_as_golden(meta):
+        assert toks == gold["tokens"].tolist()
+        assert torch.equal(torch.tensor(sum(logprobs, []), dtype=torch.float64), gold["logprobs"])
+        top = torch.cat(step_logits, 0).topk(64, dim=-1)
+        assert torch.equal(top.values, gold["topk_values"])
+    else:
+        prefix = int(meta["decisive_prefix"])
+        assert toks[0][:prefix] == gold["tokens"][0].tolist()[:prefix]
