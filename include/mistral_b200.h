@@ -161,6 +161,56 @@ int mb200_logprob_gather(const float* logits, const int64_t* target_dev, float* 
 int mb200_sample_top_p(const float* logits, const float* uniform_dev, int64_t* out_dev, int64_t T, int64_t vocab,
                        float temperature, float top_p, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mixture of experts for T > 1 tokens (prefill, batched decode).  Replaces MoeLayer.forward (moe.py:24-32): the gate Linear,
+ * torch.topk on the bf16 router logits, the fp32 softmax over the k selected, and the per-expert torch.where / gather /
+ * FeedForward / weighted `results[idx] +=` loop (one host sync per expert) -- with no host round trip at all.
+ *
+ * mb200_moe_sizes:   buffer sizes for T tokens: tile_rows (m-tile height of the grouped GEMMs: 32 / 64 for decode-sized batches,
+ *                    128 otherwise), rows_cap (rows of xs / g / yw / row_w: every expert's segment is padded to a multiple of
+ *                    tile_rows), plan_words (int32 words of `plan`).
+ * mb200_moe_route:   router + routing plan + gather.
+ *     hn [T, dim] bf16 = ffn_norm(h); gate_w [E, dim] bf16 (moe.py:20)
+ *     sel [T, k] int32, wts [T, k] bf16: the selected experts of each token in ASCENDING expert index with their routing weights
+ *     slot [T, k] int32: row of each (token, expert) pair in the expert-sorted buffers (deterministic: token order per expert)
+ *     plan [plan_words] int32: device-side description of the grouped GEMMs' m tiles (count, expert and first row of each)
+ *     xs [rows_cap, dim] bf16: hn rows gathered by slot; row_w [rows_cap] bf16: routing weight of each row
+ *     shard_rank / shard_world: expert parallelism, this rank owns the experts e % shard_world == shard_rank (1 rank: 0 / 1);
+ *     slots are numbered over ALL experts on every rank, tiles and gathered rows cover the local experts only.
+ * mb200_moe_grouped_ffn: grouped gate/up GEMM (+ SiLU*mul) -> grouped down GEMM whose epilogue rounds the expert output to bf16,
+ *     scales by the routing weight, rounds again (moe.py:31) and stores the row locally AND on every peer (comm->peer_yw: NVLink
+ *     stores, the expert-parallel exchange is this epilogue) -> combine: out[t] = residual[t] + sum over the token's k rows in
+ *     ascending expert index, every step rounded to bf16 like the reference's `+=`.
+ *     w13_host / w2_host: HOST arrays of E device pointers (packed gate/up [2*hidden, dim] and down [dim, hidden] of each expert;
+ *     NULL for experts of other ranks).  g [rows_cap, hidden], yw [rows_cap, dim] bf16 scratch; out [T, dim]; residual may be NULL.
+ *     comm: NULL when unsharded; otherwise the mapped peer buffers and the handshake words (see mb200_comm_* below).  The combine
+ *     kernel signals every peer that this rank's rows are written and waits for every peer's signal; `epoch` counts the calls.
+ */
+typedef struct mb200_moe_comm {
+  int32_t n_ranks, my_rank;
+  void* peer_yw[8];     /* yw buffer of the other ranks (mapped), n_ranks - 1 entries */
+  void* my_flags;       /* uint32 [n_ranks] in this rank's comm buffer: flags[r] written by rank r */
+  void* peer_flags[8];  /* the same array on the other ranks (mapped), n_ranks - 1 entries */
+  void* epoch;          /* uint32 device word, local: number of completed calls on this buffer */
+  void* done_counter;   /* int32 device word, local, zero */
+} mb200_moe_comm;
+int mb200_moe_sizes(int64_t T, int64_t n_experts, int64_t top_k, int64_t* tile_rows, int64_t* rows_cap, int64_t* plan_words);
+int mb200_moe_route(const void* hn, const void* gate_w, int64_t T, int64_t dim, int64_t n_experts, int64_t top_k, int64_t shard_rank,
+                    int64_t shard_world, int32_t* sel, void* wts, int32_t* slot, int32_t* plan, void* xs, void* row_w, void* stream);
+int mb200_moe_grouped_ffn(const void* xs, const void* const* w13_host, const void* const* w2_host, const int32_t* plan, const void* row_w,
+                          const int32_t* slot, const void* residual, void* g, void* yw, void* out, int64_t T, int64_t dim,
+                          int64_t hidden, int64_t n_experts, int64_t top_k, const mb200_moe_comm* comm, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Buffers that other ranks (one process per GPU) can write: plain cudaMalloc + CUDA IPC.  alloc zero-fills and synchronises;
+ * export writes the 64-byte IPC handle to pass to the other processes (e.g. torch.distributed.all_gather_object); open maps a
+ * peer's buffer into this process (peer access over NVLink is enabled lazily).  These are the only entry points that allocate. */
+int mb200_comm_alloc(size_t bytes, void** ptr_out);
+int mb200_comm_free(void* ptr);
+int mb200_comm_export(void* ptr, void* handle_out64);
+int mb200_comm_open(const void* handle64, void** ptr_out);
+int mb200_comm_close(void* ptr);
+
 /* Upper bound of the scratch any entry point above needs for up to T tokens of this geometry. */
 size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
                              int64_t hidden, int64_t vocab, int64_t max_batch);

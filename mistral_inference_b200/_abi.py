@@ -41,6 +41,16 @@ _SIGNATURES = {
     "mb200_argmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "mb200_logprob_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "mb200_sample_top_p": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p]),
+    "mb200_moe_sizes": (c_int, [c_int64, c_int64, c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "mb200_moe_route": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    "mb200_moe_grouped_ffn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mb200_comm_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "mb200_comm_free": (c_int, [c_void_p]),
+    "mb200_comm_export": (c_int, [c_void_p, c_void_p]),
+    "mb200_comm_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "mb200_comm_close": (c_int, [c_void_p]),
     "mb200_workspace_bytes": (c_size_t, [c_int64] * 8),
     "mb200_decode_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, c_int64, c_void_p,
@@ -98,10 +108,39 @@ def _stream() -> int:
 
 class Workspace:
     """Caller-owned scratch handed to every entry point (zero-filled once: the first 64 KiB hold self-resetting
-    counters, see MB200_WORKSPACE_HEADER_BYTES)."""
+    counters, see MB200_WORKSPACE_HEADER_BYTES).  Also owns the model-wide mixture-of-experts row buffers and, for an
+    expert-parallel model, the NVLink peer memory of the group (mistral_inference_b200/moe.py)."""
 
     def __init__(self, nbytes: int, device: torch.device):
         self.buf = torch.zeros(max(int(nbytes), WORKSPACE_HEADER_BYTES + 256), dtype=torch.uint8, device=device)
+        self._moe: dict = {}
+        self._comm = None
+
+    def moe_buffers(self, T: int, dim: int, hidden: int, E: int, k: int, dtype: torch.dtype, comm=None, parity: int = 0):
+        from .moe import MoeBuffers
+
+        key = (T, dim, hidden, E, k, parity if comm is not None else 0, id(comm))
+        b = self._moe.get(key)
+        if b is None:
+            if len(self._moe) >= 8:  # prompt chunks of many different lengths: keep the pool small
+                self._moe.clear()
+            yw_ptr = comm.yw_ptr(parity) if comm is not None else None
+            b = self._moe[key] = MoeBuffers(T, dim, hidden, E, k, self.buf.device, dtype, yw_ptr=yw_ptr)
+        return b
+
+    def expert_comm(self, layer, T: int, dim: int):
+        """The group's peer memory, (re)created collectively when a call needs more rows than it holds."""
+        from .moe import ExpertComm
+
+        _, rows_cap, _ = moe_sizes(T, layer.args.num_experts, layer.args.num_experts_per_tok)
+        if self._comm is None or self._comm.rows_cap < rows_cap or self._comm.dim != dim:
+            if self._comm is not None:
+                torch.cuda.synchronize()
+                self._comm.close()
+                self._moe.clear()
+            g, G = layer.expert_shard
+            self._comm = ExpertComm(g, G, layer.expert_group, rows_cap, dim, self.buf.device)
+        return self._comm
 
     @property
     def ptr(self) -> int:
@@ -200,6 +239,60 @@ def sample_top_p(logits: torch.Tensor, uniform: torch.Tensor, temperature: float
     out = torch.empty(T, dtype=torch.long, device=logits.device) if out is None else out
     _check(lib().mb200_sample_top_p(_ptr(logits), _ptr(uniform), _ptr(out), T, V, temperature, top_p, _stream()), "mb200_sample_top_p")
     return out
+
+
+class MoeCommStruct(ctypes.Structure):
+    """mb200_moe_comm (include/mistral_b200.h)."""
+    _fields_ = [("n_ranks", ctypes.c_int32), ("my_rank", ctypes.c_int32), ("peer_yw", c_void_p * 8), ("my_flags", c_void_p),
+                ("peer_flags", c_void_p * 8), ("epoch", c_void_p), ("done_counter", c_void_p)]
+
+
+def moe_sizes(T: int, E: int, k: int):
+    tr, rc, pw = c_int64(0), c_int64(0), c_int64(0)
+    _check(lib().mb200_moe_sizes(T, E, k, ctypes.byref(tr), ctypes.byref(rc), ctypes.byref(pw)), "mb200_moe_sizes")
+    return tr.value, rc.value, pw.value
+
+
+def moe_route(hn: torch.Tensor, gate_w: torch.Tensor, E: int, k: int, shard_rank: int, shard_world: int, b) -> None:
+    """Router + row plan + gather into the buffers `b` (moe.MoeBuffers)."""
+    T, dim = hn.shape
+    _check(lib().mb200_moe_route(_ptr(hn), _ptr(gate_w), T, dim, E, k, shard_rank, shard_world, _ptr(b.sel), _ptr(b.wts), _ptr(b.slot), _ptr(b.plan),
+                                 _ptr(b.xs), _ptr(b.row_w), _stream()), "mb200_moe_route")
+
+
+def moe_grouped_ffn(b, w13_host, w2_host, residual: Optional[torch.Tensor], out: torch.Tensor, T: int, dim: int, hidden: int, E: int, k: int,
+                    comm: Optional[MoeCommStruct], ws: "Workspace") -> None:
+    _check(lib().mb200_moe_grouped_ffn(_ptr(b.xs), ctypes.cast(w13_host, c_void_p), ctypes.cast(w2_host, c_void_p), _ptr(b.plan), _ptr(b.row_w),
+                                       _ptr(b.slot), _ptr(residual), _ptr(b.g), b.yw_ptr, _ptr(out), T, dim, hidden, E, k,
+                                       ctypes.cast(ctypes.pointer(comm), c_void_p) if comm is not None else None, ws.ptr, ws.nbytes, _stream()),
+           "mb200_moe_grouped_ffn")
+
+
+def comm_alloc(nbytes: int) -> int:
+    p = c_void_p(0)
+    _check(lib().mb200_comm_alloc(nbytes, ctypes.byref(p)), "mb200_comm_alloc")
+    return int(p.value)
+
+
+def comm_free(ptr: int) -> None:
+    _check(lib().mb200_comm_free(ptr), "mb200_comm_free")
+
+
+def comm_export(ptr: int) -> bytes:
+    h = ctypes.create_string_buffer(64)
+    _check(lib().mb200_comm_export(ptr, ctypes.cast(h, c_void_p)), "mb200_comm_export")
+    return h.raw
+
+
+def comm_open(handle: bytes) -> int:
+    h = ctypes.create_string_buffer(handle, 64)
+    p = c_void_p(0)
+    _check(lib().mb200_comm_open(ctypes.cast(h, c_void_p), ctypes.byref(p)), "mb200_comm_open")
+    return int(p.value)
+
+
+def comm_close(ptr: int) -> None:
+    _check(lib().mb200_comm_close(ptr), "mb200_comm_close")
 
 
 def decode_meta(seqpos_dev: torch.Tensor, meta_dev: torch.Tensor, windows) -> None:

@@ -1,5 +1,7 @@
 // libmb200.so -- the C ABI declared in include/mistral_b200.h.  Argument checking + kernel dispatch only.
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "attn_decode.cuh"
 #include "attn_prefill.cuh"
@@ -7,7 +9,9 @@
 #include "decode_megakernel.cuh"
 #include "elementwise.cuh"
 #include "gemm_mma.cuh"
+#include "gemm_streamk.cuh"
 #include "gemm_tcgen05.cuh"
+#include "moe.cuh"
 #include "sampling.cuh"
 #include "skinny_linear.cuh"
 
@@ -44,9 +48,9 @@ static int run_linear(const void* x, const void* norm_w, const void* w, const Ep
   }
   const void* a = x;
   if (norm_w) {
-    const size_t need = kWsHeader + align256((size_t)T * K * 2);
+    const size_t need = kWsHeader + SK_PARTIAL_BYTES + align256((size_t)T * K * 2);
     if (workspace == nullptr || workspace_bytes < need) return fail(MB200_E_WORKSPACE, "linear: workspace %zu < %zu", workspace_bytes, need);
-    void* normed = (uint8_t*)workspace + kWsHeader;
+    void* normed = (uint8_t*)workspace + kWsHeader + SK_PARTIAL_BYTES;  // after the stream-K partial slots
     int rc = run_rmsnorm(x, norm_w, normed, T, K, eps, st);
     if (rc) return rc;
     a = normed;
@@ -58,6 +62,7 @@ static int run_linear(const void* x, const void* norm_w, const void* w, const Ep
   g.N = (int)N;
   g.K = (int)K;
   g.epi = epi;
+  if (streamk_eligible(T, N, K)) return launch_streamk<MODE>(g, workspace, workspace_bytes, kWsHeader, st);  // decode-sized batches: HBM-bound
   if (tcgen05_gemm_eligible(T, N, K)) return launch_gemm_tcgen05<MODE>(g, st);
   return launch_gemm_mma<MODE>(g, st);
 }
@@ -85,6 +90,7 @@ size_t mb200_workspace_bytes(int64_t T, int64_t dim, int64_t n_heads, int64_t n_
   const int64_t widest = dim > hidden ? dim : hidden;
   const int64_t rep = n_kv_heads > 0 ? n_heads / n_kv_heads : 1;
   size_t s = kWsHeader;
+  s += SK_PARTIAL_BYTES;                                                  // stream-K partial accumulators (decode-sized GEMMs)
   s += align256((size_t)T * widest * 2);                                  // normed activations
   s += attn_decode_workspace(max_batch, n_kv_heads, 64, rep);             // split-KV partials (n_splits <= 64)
   // decode_step scratch (residual ping-pong, h, q, attn, g) lives in the same region as the normed activations
@@ -280,6 +286,142 @@ int mb200_sample_top_p(const float* logits, const float* uniform_dev, int64_t* o
   sample_top_p_kernel<<<(unsigned)T, SP_THREADS, 0, (cudaStream_t)stream>>>(logits, uniform_dev, (long long*)out_dev, (int)vocab,
                                                                             1.0f / temperature, top_p);
   MB_CHECK_LAUNCH("sample_top_p_kernel");
+  return MB200_OK;
+}
+
+// ---- mixture of experts (csrc/moe.cuh) ---------------------------------------------------------------------------------------
+int mb200_moe_sizes(int64_t T, int64_t n_experts, int64_t top_k, int64_t* tile_rows, int64_t* rows_cap, int64_t* plan_words) {
+  MB_CHECK_ARG(T >= 1 && n_experts >= 1 && top_k >= 1, "moe_sizes: bad arguments");
+  const int tr = moe_tile_rows(T);
+  const int64_t cap = moe_tile_cap(T * top_k, n_experts, tr);
+  if (tile_rows) *tile_rows = tr;
+  if (rows_cap) *rows_cap = cap * tr;
+  if (plan_words) *plan_words = MOE_PLAN_HEADER + 2 * cap;
+  return MB200_OK;
+}
+
+int mb200_moe_route(const void* hn, const void* gate_w, int64_t T, int64_t dim, int64_t n_experts, int64_t top_k, int64_t shard_rank,
+                    int64_t shard_world, int32_t* sel, void* wts, int32_t* slot, int32_t* plan, void* xs, void* row_w, void* stream) {
+  MB_CHECK_ARG(hn && gate_w && sel && wts && slot && plan && xs && row_w, "moe_route: null pointer");
+  MB_CHECK_ARG(T >= 1 && dim % 8 == 0, "moe_route: T=%lld dim=%lld", (long long)T, (long long)dim);
+  MB_CHECK_ARG(top_k >= 1 && top_k <= MOE_MAX_TOPK && top_k <= n_experts && n_experts <= MOE_MAX_EXPERTS,
+               "moe_route: E=%lld (max %d), k=%lld (max %d)", (long long)n_experts, MOE_MAX_EXPERTS, (long long)top_k, MOE_MAX_TOPK);
+  MB_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "moe_route: shard %lld of %lld", (long long)shard_rank,
+               (long long)shard_world);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)ceil_div(T, 8);
+  switch (n_experts) {
+    case 2: moe_route_kernel<2><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
+    case 4: moe_route_kernel<4><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
+    case 8: moe_route_kernel<8><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
+    case 16: moe_route_kernel<16><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
+    default: return fail(MB200_E_INVALID, "moe_route: n_experts=%lld unsupported (2, 4, 8, 16)", (long long)n_experts);
+  }
+  MB_CHECK_LAUNCH("moe_route_kernel");
+  const int tile_rows = moe_tile_rows(T);
+  const int64_t pairs = T * top_k, cap = moe_tile_cap(pairs, n_experts, tile_rows);
+  const size_t plan_smem = ((size_t)n_experts * MP_THREADS + 2 * n_experts + 1) * sizeof(int32_t);
+  MB_CHECK_CUDA(cudaFuncSetAttribute(moe_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
+  moe_plan_kernel<<<1, MP_THREADS, plan_smem, st>>>(sel, (int)pairs, (int)n_experts, tile_rows, (int)shard_rank, (int)shard_world, (int)cap, slot, plan);
+  MB_CHECK_LAUNCH("moe_plan_kernel");
+  moe_gather_kernel<<<(unsigned)ceil_div(pairs, 8), 256, 0, st>>>((const uint4*)hn, sel, (const bf16*)wts, slot, (int)pairs, (int)top_k, (int)(dim / 8),
+                                                                  (int)shard_rank, (int)shard_world, (uint4*)xs, (bf16*)row_w);
+  MB_CHECK_LAUNCH("moe_gather_kernel");
+  return MB200_OK;
+}
+
+int mb200_moe_grouped_ffn(const void* xs, const void* const* w13_host, const void* const* w2_host, const int32_t* plan, const void* row_w,
+                          const int32_t* slot, const void* residual, void* g, void* yw, void* out, int64_t T, int64_t dim, int64_t hidden,
+                          int64_t n_experts, int64_t top_k, const mb200_moe_comm* comm, void* workspace, size_t workspace_bytes, void* stream) {
+  MB_CHECK_ARG(xs && w13_host && w2_host && plan && row_w && slot && g && yw && out, "moe_grouped_ffn: null pointer");
+  MB_CHECK_ARG(T >= 1 && top_k >= 1 && top_k <= MOE_MAX_TOPK && n_experts <= MOE_MAX_EXPERTS && dim % 64 == 0 && hidden % 64 == 0,
+               "moe_grouped_ffn: T=%lld k=%lld E=%lld dim=%lld hidden=%lld", (long long)T, (long long)top_k, (long long)n_experts, (long long)dim,
+               (long long)hidden);
+  const int n_ranks = comm ? comm->n_ranks : 1, my_rank = comm ? comm->my_rank : 0;
+  MB_CHECK_ARG(n_ranks >= 1 && n_ranks <= kMaxPeers && my_rank >= 0 && my_rank < n_ranks, "moe_grouped_ffn: rank %d of %d", my_rank, n_ranks);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tile_rows = moe_tile_rows(T);
+  const int64_t pairs = T * top_k, rows_cap = moe_row_cap(pairs, n_experts, tile_rows);
+  int local = 0;
+  for (int e = 0; e < (int)n_experts; ++e) local += (w13_host[e] != nullptr);
+  MB_CHECK_ARG(local >= 1, "moe_grouped_ffn: this rank owns no expert");
+  // expected number of this rank's experts that get at least one row (uniform routing): sizes the decode tile width
+  double touched = (double)n_experts * (1.0 - pow(1.0 - (double)top_k / (double)n_experts, (double)T)) * ((double)local / (double)n_experts);
+  int est = (int)(touched + 0.5);
+  if (est < 1) est = 1;
+  if (tile_rows == 128) est = (int)((pairs / n_ranks + tile_rows - 1) / tile_rows) + local;
+  EpiParams e1;
+  e1.out = g;
+  e1.ld_out = hidden;
+  int rc = launch_grouped<EPI_SWIGLU>(xs, rows_cap, dim, 2 * hidden, w13_host, (int)n_experts, est, tile_rows, plan, e1, workspace, workspace_bytes, kWsHeader, st);
+  if (rc) return rc;
+  EpiParams e2;
+  e2.out = yw;
+  e2.ld_out = dim;
+  e2.row_w = row_w;
+  e2.n_peers = n_ranks - 1;
+  for (int r = 0; r < n_ranks - 1; ++r) {
+    MB_CHECK_ARG(comm->peer_yw[r] != nullptr, "moe_grouped_ffn: peer buffer %d missing", r);
+    e2.peer_out[r] = comm->peer_yw[r];
+  }
+  rc = launch_grouped<EPI_MOE_SCALE>(g, rows_cap, hidden, dim, w2_host, (int)n_experts, est, tile_rows, plan, e2, workspace, workspace_bytes, kWsHeader, st);
+  if (rc) return rc;
+  MoeCombineParams c;
+  c.yw = (const uint4*)yw;
+  c.slot = slot;
+  c.residual = (const uint4*)residual;
+  c.out = (uint4*)out;
+  c.T = (int)T;
+  c.k = (int)top_k;
+  c.row_chunks = (int)(dim / 8);
+  c.n_ranks = n_ranks;
+  c.my_rank = my_rank;
+  c.my_flags = nullptr;
+  c.epoch = nullptr;
+  c.done_counter = nullptr;
+  for (int r = 0; r < kMaxPeers; ++r) c.peer_flags[r] = nullptr;
+  if (n_ranks > 1) {
+    MB_CHECK_ARG(comm->my_flags && comm->epoch && comm->done_counter, "moe_grouped_ffn: comm state missing");
+    c.my_flags = (unsigned*)comm->my_flags;
+    c.epoch = (unsigned*)comm->epoch;
+    c.done_counter = (int*)comm->done_counter;
+    for (int r = 0; r < n_ranks - 1; ++r) {
+      MB_CHECK_ARG(comm->peer_flags[r] != nullptr, "moe_grouped_ffn: peer flags %d missing", r);
+      c.peer_flags[r] = (unsigned*)comm->peer_flags[r];
+    }
+  }
+  moe_combine_kernel<<<(unsigned)T, 128, 0, st>>>(c);
+  MB_CHECK_LAUNCH("moe_combine_kernel");
+  return MB200_OK;
+}
+
+// ---- NVLink peer buffers for the expert-parallel exchange: plain CUDA IPC on cudaMalloc'ed memory ------------------------------
+int mb200_comm_alloc(size_t bytes, void** ptr_out) {
+  MB_CHECK_ARG(ptr_out && bytes > 0, "comm_alloc: bad arguments");
+  MB_CHECK_CUDA(cudaMalloc(ptr_out, bytes));
+  MB_CHECK_CUDA(cudaMemset(*ptr_out, 0, bytes));
+  MB_CHECK_CUDA(cudaDeviceSynchronize());
+  return MB200_OK;
+}
+int mb200_comm_free(void* ptr) {
+  if (ptr) MB_CHECK_CUDA(cudaFree(ptr));
+  return MB200_OK;
+}
+int mb200_comm_export(void* ptr, void* handle_out64) {
+  MB_CHECK_ARG(ptr && handle_out64, "comm_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  MB_CHECK_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out64, ptr));
+  return MB200_OK;
+}
+int mb200_comm_open(const void* handle64, void** ptr_out) {
+  MB_CHECK_ARG(handle64 && ptr_out, "comm_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  MB_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return MB200_OK;
+}
+int mb200_comm_close(void* ptr) {
+  if (ptr) MB_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
   return MB200_OK;
 }
 

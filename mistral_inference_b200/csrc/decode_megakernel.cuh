@@ -38,10 +38,14 @@ constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
 constexpr int MK_PRODUCER_WARPS = MB200_MK_PRODUCERS;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
 // The producers sit in their own warpgroup (4 warps, the last ones idle) so that setmaxnreg can move registers from it to the two
 // consumer warpgroups: 384 threads launch with 168 registers each (3 warps per SM sub-partition), then the producer warpgroup
-// drops to MK_PRODUCER_REGS and the consumers grow to MK_CONSUMER_REGS (64 + 2 x 224 = 512 = one sub-partition's file / 32).
+// drops to MK_PRODUCER_REGS and the consumers grow to MK_CONSUMER_REGS.  setmaxnreg.inc can only take what the CTA itself gave
+// back (the SM's unallocated remainder is NOT in the CTA pool -- asking for more blocks forever: the consumers never start and the
+// producers stall on a full ring): (168 - 120) x 128 threads released = (192 - 168) x 256 threads acquired, exactly (the consumers need ~188, the producers ~60).
 constexpr int MK_THREADS = MK_CONSUMERS + 128;
-#define MK_PRODUCER_REGS 64
-#define MK_CONSUMER_REGS 224
+#define MK_LAUNCH_REGS 168
+#define MK_PRODUCER_REGS 120
+#define MK_CONSUMER_REGS 192
+static_assert((MK_LAUNCH_REGS - MK_PRODUCER_REGS) * 128 >= (MK_CONSUMER_REGS - MK_LAUNCH_REGS) * MK_CONSUMERS, "setmaxnreg pool");
 #define MK_STR2(x) #x
 #define MK_STR(x) MK_STR2(x)
 static_assert(MB200_MK_PRODUCERS <= 4, "one producer warpgroup");

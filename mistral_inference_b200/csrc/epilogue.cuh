@@ -13,7 +13,10 @@ enum EpiMode : int {
   EPI_F32 = 2,       // logits[t, n] = float(bf16(acc))                           (transformer.py:235,240)
   EPI_SWIGLU = 3,    // g[t, n/2] = bf16( bf16(silu(bf16(acc0))) * bf16(acc1) )   (transformer_layers.py:106)
   EPI_QKV_ROPE = 4,  // split into q/k/v, rotate q,k pairs, optional ring scatter  (transformer_layers.py:66-70, cache.py:91-92)
+  EPI_MOE_SCALE = 5, // yw[row, n] = bf16( w[row] * bf16(acc) ), stored on every rank of an expert-parallel group  (moe.py:31)
 };
+
+constexpr int kMaxPeers = 8;
 
 struct EpiParams {
   void* out = nullptr;             // bf16 [T, ld_out]
@@ -30,6 +33,11 @@ struct EpiParams {
   const int32_t* cache_rows = nullptr;  // [T] or null
   const float* rope = nullptr;          // [n_pos, 64, 2]
   int q_dim = 0, kv_dim = 0;
+  // EPI_MOE_SCALE: routing weight of each (token, expert) row; the weighted expert output goes to `out` and to the same offset
+  // of the mapped buffers of the other ranks (NVLink peer stores; n_peers == 0 when unsharded)
+  const void* row_w = nullptr;  // bf16 [rows]
+  void* peer_out[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0;
 };
 
 template <int MODE>
@@ -47,6 +55,12 @@ __device__ __forceinline__ void epi_pair(const EpiParams& p, int t, int n, float
   } else if constexpr (MODE == EPI_SWIGLU) {
     const float s = round_bf16(ref_silu(y0));
     reinterpret_cast<bf16*>(p.out)[(int64_t)t * p.ld_out + (n >> 1)] = __float2bfloat16_rn(s * y1);
+  } else if constexpr (MODE == EPI_MOE_SCALE) {
+    const float w = bf16_to_float(reinterpret_cast<const uint16_t*>(p.row_w)[t]);
+    const uint32_t packed = pack_bf16x2(w * y0, w * y1);
+    const int64_t off = (int64_t)t * p.ld_out + n;
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + off) = packed;
+    for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.peer_out[r]) + off) = packed;
   } else if constexpr (MODE == EPI_QKV_ROPE) {
     if (n < p.q_dim + p.kv_dim) {  // q or k: rotate
       const int pos = p.positions[t];
@@ -109,6 +123,20 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int t, int n, co
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else if constexpr (MODE == EPI_MOE_SCALE) {
+    const float w = bf16_to_float(reinterpret_cast<const uint16_t*>(p.row_w)[t]);
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = pack2_rn(w * round_bf16(__uint_as_float(v[2 * j])), w * round_bf16(__uint_as_float(v[2 * j + 1])));
+    const int64_t off = (int64_t)t * p.ld_out + n;
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + off);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    for (int r = 0; r < p.n_peers; ++r) {  // the same row on the other ranks (NVLink peer stores, 64 B per thread and chunk)
+      uint4* pd = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.peer_out[r]) + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pd[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
   } else if constexpr (MODE == EPI_F32) {
     float4* dst = reinterpret_cast<float4*>(p.out_f32 + (int64_t)t * p.ld_out + n);
 #pragma unroll

@@ -1,0 +1,268 @@
+// Weight-streaming GEMM for decode-sized batches (5 <= T <= 128 tokens):  C[T, N] = A[T, K] * W[N, K]^T, bound by HBM.
+//
+// At these sizes the step reads every weight byte once and does ~2T flop per byte: the kernel's only job is to keep all 148 SMs
+// pulling their share of W at the HBM rate.  Two measured facts shape it (B200, Nemo-12B shapes, batch 32):
+//   * tile width: a W stage of [128 rows x 64] = 16 KB streams at the full HBM rate (lm head: 1.34 GB in 205 us), [64 x 64] gets
+//     ~40 % and [32 x 64] ~26 %: per stage the one-thread TMA producer and the one-thread MMA issuer each spend a few hundred
+//     cycles, so a stage must carry >= 16 KB.  Tiles are therefore always 128 wide;
+//   * N / 128 tiles do not divide over 148 SMs (wo of Nemo: 40 tiles; gate/up: 224 = 1.5 rounds), so the work is cut stream-K
+//     style instead: the (tile, k-block) units of the whole problem are one sequence, and CTA c takes the c-th contiguous 1/G of
+//     it -- every SM streams the same number of bytes (+- one 16 KB stage) in one pass, whatever N and K are.
+// A CTA's range covers the tail of one tile, some whole tiles and the head of another.  Partial tiles are reduced
+// deterministically: a contributor that does not own the tile's first k-block writes its fp32 accumulator to its own slot of the
+// workspace and raises a flag; the owner of the first k-block -- for which this tile is the LAST thing it does, long after the
+// others did theirs FIRST -- adds the partials in ascending k order and runs the epilogue.  No atomics on data, no host-visible
+// state: flags are consumed (reset) by their single reader.
+//
+// Structure per CTA is that of gemm_tcgen05.cuh: warp 0 TMA producer ([TA x 64] A box + [128 x 64] W box per stage, deep ring),
+// warp 1 tcgen05.mma issuer (M = 128 -- rows >= TA read past the short A box and are never stored --, N = 128, fp32 accumulators
+// double-buffered in TMEM), warps 2-5 epilogue (epilogue.cuh row-chunk epilogues).  GROUPED: the mixture-of-experts variant -- m
+// tiles (expert segments of <= TA rows) come from the device-side plan of csrc/moe.cuh, each with its own weight tensor map.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace mb200 {
+
+constexpr int SK_BN = 128;
+constexpr int SK_MAX_CTAS = 160;
+constexpr size_t SK_PARTIAL_BYTES = (size_t)SK_MAX_CTAS * 128 * SK_BN * sizeof(float);  // one [128 x 128] fp32 slot per CTA
+constexpr size_t SK_FLAGS_OFFSET = 24576;  // inside the zero-initialised workspace header: uint32 flags[SK_MAX_CTAS]
+
+struct SkParams {
+  int T, N, K;
+  EpiParams epi;
+  float* partials;  // [gridDim][TA][128] fp32
+  unsigned* flags;  // [gridDim], zero between launches
+};
+
+template <int MODE, int TA, bool GROUPED>
+__device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUtensorMap* map_w_base, const SkParams& p, const int32_t* plan) {
+  using Cfg = TgCfg<SK_BN, TA>;
+  constexpr int STAGES = Cfg::kStages, STAGE_BYTES = Cfg::kStageBytes, A_BYTES = Cfg::kABytes, TMEM_COLS = Cfg::kTmemCols;
+  constexpr uint32_t kIdesc = Cfg::kIdesc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + Cfg::kSlack);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int num_m = GROUPED ? plan[0] : 1, num_n = p.N / SK_BN, num_k = p.K / TG_BK;
+  const int32_t* tile_expert = GROUPED ? plan + MOE_PLAN_HEADER : nullptr;
+  const int32_t* tile_row0 = GROUPED ? plan + MOE_PLAN_HEADER + plan[2] : nullptr;
+  // unit u = (tile, k-block) = (u / num_k, u % num_k); CTA c owns units [first(c), first(c + 1))
+  const long long total = (long long)num_m * num_n * num_k;
+  const long long per = total / G, rem = total % G;
+  auto first = [&](int c) { return (long long)c * per + (c < rem ? c : rem); };
+  const long long u_begin = first(cta), u_end = first(cta + 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = u_begin; u < u_end;) {
+        const int tile = (int)(u / num_k), kb0 = (int)(u % num_k);
+        const int kb1 = (int)min((long long)num_k, kb0 + (u_end - u));
+        const int m0 = GROUPED ? tile_row0[tile % num_m] : 0, n0 = (tile / num_m) * SK_BN;
+        const CUtensorMap* wmap = GROUPED ? map_w_base + tile_expert[tile % num_m] : map_w_base;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+          mbar_wait(&empty[s], par ^ 1, 21, it);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, m0);
+          tma_load_2d(sa + A_BYTES, wmap, &full[s], kb * TG_BK, n0);
+        }
+        u += kb1 - kb0;
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      uint32_t it = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int kb0 = (int)(u % num_k);
+        const int kb1 = (int)min((long long)num_k, kb0 + (u_end - u));
+        const uint32_t acc = seg & 1, acc_par = (seg >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_par ^ 1, 22, seg);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * SK_BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+          mbar_wait(&full[s], par, 23, it);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (kb > kb0 || k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+        u += kb1 - kb0;
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. + 31 =================
+    const int lane_base = (warp & 3) * 32;
+    const bool row_ok = TA == 128 || lane_base + lane < TA;  // accumulator rows >= TA come from beyond the short A box
+    const int etid = (int)threadIdx.x - 64;                  // 0..127 among the epilogue threads
+    uint32_t seg = 0;
+    for (long long u = u_begin; u < u_end; ++seg) {
+      const int tile = (int)(u / num_k), kb0 = (int)(u % num_k);
+      const int kb1 = (int)min((long long)num_k, kb0 + (u_end - u));
+      const int m0 = GROUPED ? tile_row0[tile % num_m] : 0, n0 = (tile / num_m) * SK_BN;
+      const uint32_t acc = seg & 1, acc_par = (seg >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_par, 24, seg);
+      tc_fence_after();
+      const int t = row_ok ? m0 + lane_base + lane : 0x7fffffff;
+      const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * SK_BN;
+      uint32_t v[32];
+      if (kb0 != 0) {
+        // ---- contributor: park the fp32 accumulator in this CTA's slot, then raise the flag ----
+        if (lane_base < TA) {
+          float* mine = p.partials + ((size_t)cta * TA + lane_base + lane) * SK_BN;
+#pragma unroll 1
+          for (int c = 0; c < SK_BN / 32; ++c) {
+            tmem_ld_32x32b_x32(trow + c * 32, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<uint4*>(mine + c * 32)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (etid == 0) st_release_u32(p.flags + cta, 1u);
+      } else if (kb1 != num_k) {
+        // ---- owner of the first k-block of a tile others finish: wait for them (they did it first thing), add in k order ----
+        const long long tile_end = (long long)(tile + 1) * num_k;
+        int last = cta;
+        while (last + 1 < G && first(last + 1) < tile_end) ++last;
+        if (etid == 0) {
+          for (int c = cta + 1; c <= last; ++c) {
+            unsigned spins = 0;
+            while (ld_acquire_u32(p.flags + c) == 0u) {
+              if (++spins == MB200_WATCHDOG_SPINS) {
+                printf("[mb200 watchdog] stream-K block %d waits for the partial of block %d (tile %d)\n", cta, c, tile);
+                __trap();
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < SK_BN / 32; ++c) {
+          tmem_ld_32x32b_x32(trow + c * 32, v);
+          if (lane_base < TA) {
+            for (int o = cta + 1; o <= last; ++o) {
+              const float* theirs = p.partials + ((size_t)o * TA + lane_base + lane) * SK_BN + c * 32;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint4 w = __ldcg(reinterpret_cast<const uint4*>(theirs) + q);
+                v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + __uint_as_float(w.x));
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + __uint_as_float(w.y));
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + __uint_as_float(w.z));
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + __uint_as_float(w.w));
+              }
+            }
+          }
+          if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (etid == 0)
+          for (int c = cta + 1; c <= last; ++c) p.flags[c] = 0u;  // consumed: ready for the next launch
+      } else {
+        // ---- whole tile in this CTA ----
+#pragma unroll 1
+        for (int c = 0; c < SK_BN / 32; ++c) {
+          tmem_ld_32x32b_x32(trow + c * 32, v);
+          if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      u += kb1 - kb0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int MODE, int TA>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+    gemm_streamk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const SkParams p) {
+  sk_gemm_body<MODE, TA, false>(map_a, &map_w, p, nullptr);
+}
+
+template <int MODE, int TA>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+    gemm_streamk_grouped_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ MoeWeightMaps maps_w, const SkParams p,
+                                const int32_t* __restrict__ plan) {
+  sk_gemm_body<MODE, TA, true>(map_a, maps_w.m, p, plan);
+}
+
+inline bool streamk_eligible(int64_t T, int64_t N, int64_t K) {
+  const char* e = getenv("MB200_STREAMK");
+  if (e != nullptr && e[0] == '0') return false;
+  return T >= 1 && T <= 128 && N % SK_BN == 0 && K % TG_BK == 0;
+}
+
+// workspace: partial slots at `ws + header`, flags in the header (both overlap scratch of other, stream-ordered entry points)
+template <int MODE, int TA>
+int launch_streamk_ta(const GemmParams& g, void* workspace, size_t workspace_bytes, size_t header, cudaStream_t stream) {
+  using Cfg = TgCfg<SK_BN, TA>;
+  int dev = 0, sms = 0;
+  MB_CHECK_CUDA(cudaGetDevice(&dev));
+  MB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sms > SK_MAX_CTAS) sms = SK_MAX_CTAS;
+  if (workspace == nullptr || workspace_bytes < header + SK_PARTIAL_BYTES) return fail(MB200_E_WORKSPACE, "stream-K gemm: workspace %zu < %zu", workspace_bytes, header + SK_PARTIAL_BYTES);
+  CUtensorMap map_a, map_w;
+  int rc = make_tensor_map_2d(&map_a, g.a, g.T, g.K, TA);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&map_w, g.w, g.N, g.K, SK_BN);
+  if (rc) return rc;
+  SkParams p;
+  p.T = g.T;
+  p.N = g.N;
+  p.K = g.K;
+  p.epi = g.epi;
+  p.partials = reinterpret_cast<float*>((uint8_t*)workspace + header);
+  p.flags = reinterpret_cast<unsigned*>((uint8_t*)workspace + SK_FLAGS_OFFSET);
+  const long long units = (long long)(g.N / SK_BN) * (g.K / TG_BK);
+  const int grid = (int)(units < sms ? units : sms);
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_streamk_kernel<MODE, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  gemm_streamk_kernel<MODE, TA><<<grid, TG_THREADS, Cfg::kSmem, stream>>>(map_a, map_w, p);
+  MB_CHECK_LAUNCH("gemm_streamk_kernel");
+  return MB200_OK;
+}
+
+template <int MODE>
+int launch_streamk(const GemmParams& g, void* workspace, size_t workspace_bytes, size_t header, cudaStream_t stream) {
+  if (g.T <= 32) return launch_streamk_ta<MODE, 32>(g, workspace, workspace_bytes, header, stream);
+  if (g.T <= 64) return launch_streamk_ta<MODE, 64>(g, workspace, workspace_bytes, header, stream);
+  return launch_streamk_ta<MODE, 128>(g, workspace, workspace_bytes, header, stream);
+}
+
+}  // namespace mb200

@@ -137,10 +137,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Each CTA fetches HALF of the shared [256 x 64] W tile and TMA-multicasts it into both shared memories, so the L2 -> SM traffic
 // per CTA and k-block drops from 48 KB to 32 KB (at T = 4096 the single-CTA kernel pulls ~20 TB/s out of L2).  A stage may be
 // refilled only when BOTH CTAs' MMAs have read it: the empty barriers count two commits, each multicast to the pair.
-template <int MODE, int CL, int BN, int TA = 128>
-__global__ void __launch_bounds__(TG_THREADS, 1)
-    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
+//
+// GROUPED = true (mixture of experts, csrc/moe.cuh): the A rows are the (token, expert) pairs sorted by expert, every expert's
+// segment padded to a multiple of TA rows; m tile i covers rows plan.tile_row0[i] .. + TA of expert plan.tile_expert[i], whose
+// weight matrix has its own tensor map (map_w[expert]).  The number of m tiles is DEVICE data (no host sync after routing).
+constexpr int MOE_PLAN_HEADER = 64;  // int32 words: [0] m tiles of this rank, [1] padded rows in total, [2] tile capacity, [8..] segment starts
+constexpr int MOE_MAX_EXPERTS = 16;  // tensor maps travel as kernel parameters (128 B each)
+struct MoeWeightMaps {
+  CUtensorMap m[MOE_MAX_EXPERTS];
+};
+
+template <int MODE, int CL, int BN, int TA, bool GROUPED>
+__device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUtensorMap* map_w_base, const TcGemmParams& p, const int32_t* plan) {
   static_assert(TA == 128 || CL == 1, "small-batch variant is single-CTA");
+  static_assert(!GROUPED || CL == 1, "grouped variant is single-CTA");
   using Cfg = TgCfg<BN, TA>;
   constexpr int TG_STAGES = Cfg::kStages, TG_B_BYTES = Cfg::kBBytes, TG_STAGE_BYTES = Cfg::kStageBytes, TG_TMEM_COLS = Cfg::kTmemCols;
   constexpr int TG_A_BYTES = Cfg::kABytes;  // shadows the 128-row constant
@@ -158,7 +168,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int cta = (int)blockIdx.x / CL, n_cta = (int)gridDim.x / CL;  // cluster index / clusters in the grid
   // a cluster walks "super tiles" of CL vertically adjacent tiles; rows past T read as zeros (TMA) and are never stored
-  const int num_m = ((p.T + TG_BM - 1) / TG_BM + CL - 1) / CL, num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
+  const int num_m = GROUPED ? plan[0] : ((p.T + TG_BM - 1) / TG_BM + CL - 1) / CL;
+  const int num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
+  const int32_t* tile_expert = GROUPED ? plan + MOE_PLAN_HEADER : nullptr;
+  const int32_t* tile_row0 = GROUPED ? plan + MOE_PLAN_HEADER + plan[2] : nullptr;
+  const CUtensorMap& map_w = *map_w_base;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) {
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (!GROUPED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TG_TMEM_COLS);
   tc_fence_before();
@@ -187,7 +201,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = cta; tile < num_tiles; tile += n_cta) {
-        const int m0 = ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
+        const int m0 = GROUPED ? tile_row0[tile % num_m] : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
+        const CUtensorMap* wmap = GROUPED ? map_w_base + tile_expert[tile % num_m] : map_w_base;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const uint32_t s = it % TG_STAGES, par = (it / TG_STAGES) & 1;
           mbar_wait(&empty[s], par ^ 1, 11, it);
@@ -198,7 +213,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
             tma_load_2d_multicast(sa + TG_A_BYTES + rank * (TG_B_BYTES / CL), &map_w, &full[s], kb * TG_BK, n0 + rank * (TG_BN / CL),
                                   (uint16_t)((1u << CL) - 1));
           else
-            tma_load_2d(sa + TG_A_BYTES, &map_w, &full[s], kb * TG_BK, n0);
+            tma_load_2d(sa + TG_A_BYTES, wmap, &full[s], kb * TG_BK, n0);
         }
       }
     }
@@ -233,11 +248,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
     const int lane_base = (warp & 3) * 32;
     uint32_t acc_it = 0;
     for (int tile = cta; tile < num_tiles; tile += n_cta, ++acc_it) {
-      const int m0 = ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
+      const int m0 = GROUPED ? tile_row0[tile % num_m] : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
       const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_par, 14, acc_it);
       tc_fence_after();
-      const int t = m0 + lane_base + lane;
+      // accumulator rows >= TA were computed from whatever follows the short A box in shared memory: never stored
+      const int t = (TA == 128 || lane_base + lane < TA) ? m0 + lane_base + lane : 0x7fffffff;
       // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue
       const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN;
       uint32_t va[32], vb[32];
@@ -267,6 +283,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
   else
     __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TG_TMEM_COLS);
+}
+
+template <int MODE, int CL, int BN, int TA = 128>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcGemmParams p) {
+  tc_gemm_body<MODE, CL, BN, TA, false>(map_a, &map_w, p, nullptr);
+}
+
+template <int MODE, int BN, int TA>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+    gemm_tcgen05_grouped_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ MoeWeightMaps maps_w, const TcGemmParams p,
+                                const int32_t* __restrict__ plan) {
+  tc_gemm_body<MODE, 1, BN, TA, true>(map_a, maps_w.m, p, plan);
 }
 
 // ---- host: tensor maps (driver API through the runtime's entry-point lookup, no libcuda link dependency) ----

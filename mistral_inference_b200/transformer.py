@@ -73,6 +73,9 @@ class Transformer(nn.Module):
             for i in range(offset, end)
         })
         self.n_local_layers = len(self.layers)
+        for j, blk in enumerate(self.layers.values()):  # consecutive MoE layers alternate the expert-parallel exchange buffer
+            if hasattr(blk.feed_forward, "layer_parity"):
+                blk.feed_forward.layer_parity = j & 1
         self._ws: Optional[_abi.Workspace] = None
         self._ws_tokens = 0
         self.last_argmax: Optional[torch.Tensor] = None  # device token id(s) written by the last fused-argmax decode step
@@ -222,8 +225,6 @@ class Transformer(nn.Module):
     def _graph_decode_ok(self, seqlens: List[int], cache: Optional[BufferCache]) -> bool:
         if cache is None or self.num_pipeline_ranks != 1:
             return False
-        if self.args.moe is not None and not self._megakernel_ok(len(seqlens)):
-            return False  # the per-op MoE layer has host-side routing syncs (not capturable); batch-1 decode runs in the megakernel
         if os.environ.get("MB200_DECODE_GRAPH", "1") == "0":
             return False
         host = cache._kv_seqlens_host

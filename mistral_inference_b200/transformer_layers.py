@@ -177,6 +177,5 @@ class TransformerBlock(nn.Module):
         # r = feed_forward(ffn_norm(h)); out = h + r          (transformer_layers.py:167-168)
         if isinstance(self.feed_forward, MoeLayer):
             hn = _abi.rmsnorm(h, self.ffn_norm.weight, self.norm_eps)
-            r = self.feed_forward.forward(hn, ws)
-            return h + r
+            return self.feed_forward.run(hn, h, ws)  # router + grouped experts + ordered combine + residual, no host sync
         return self.feed_forward.run(h, self.ffn_norm.weight, self.norm_eps, h, ws)

@@ -59,35 +59,56 @@ def test_replicas_timing_rule_and_pipeline_split_world2():
 
 
 def _moe_worker(rank: int, world: int, port: int, q):
-    """Expert-sharded MoE on CPU: the product's routing/combination code with the oracle's FeedForward as the
-    expert function and a gloo all-reduce, against the oracle's unsharded MoE (moe.py:24-32)."""
+    """Expert-parallel MoE on CPU, world 2: the exchange ALGORITHM of csrc/moe.cuh -- every rank derives the same
+    deterministic row plan, computes bf16(w * expert(x)) for the rows of its own experts, the rows are gathered on every rank
+    (all-gather, no reduction) and combined in ascending expert index with a bf16 rounding per step -- against the oracle's
+    unsharded MoE (moe.py:24-32), for top-2 AND top-3 (any reduction-order-free design must be exact for k > 2 as well); plus the
+    product's key filtering of an expert-sharded model."""
     sys.path.insert(0, str(REPO))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
-    import torch.nn.functional as F
-
     import mistral_inference_b200 as mi
     from mistral_inference_b200 import synth
-    from mistral_inference_b200.moe import all_reduce_partial, route_and_combine
     from mistral_inference_b200.transformer import Transformer
     from oracle import restatement as R
+    from tests.util import moe_plan_host, moe_route_host
 
     p = synth.shape("tiny-moe")
-    E, k, dim = p["moe"]["num_experts"], p["moe"]["num_experts_per_tok"], p["dim"]
+    E, dim = p["moe"]["num_experts"], p["dim"]
     sd = synth.synth_state_dict(p, 3)
     experts = [tuple(sd[f"layers.0.feed_forward.experts.{e}.{n}.weight"] for n in ("w1", "w2", "w3")) for e in range(E)]
     gate_w = sd["layers.0.feed_forward.gate.weight"]
     x = synth.synth_tensor("x", (37, dim), 5, torch.bfloat16, "cpu")
-    want = R.moe_forward(x, gate_w, experts, k)
-    local = [e for e in range(E) if e % world == rank]
-    got = route_and_combine(x, F.linear(x, gate_w), k, local, lambda e, rows: R.feed_forward(rows, *experts[e]),
-                            lambda r: all_reduce_partial(r))
+    exact = []
+    for k in (2, 3):
+        want = R.moe_forward(x, gate_w, experts, k)
+        sel, wts = moe_route_host(x, gate_w, k)
+        slot, seg, tiles = moe_plan_host(sel, E, 32, (rank, world))
+        yw = torch.zeros(seg[-1], dim, dtype=torch.bfloat16)  # this rank's rows (the down projection's epilogue output)
+        for t in range(x.shape[0]):
+            for j in range(k):
+                e = int(sel[t, j])
+                if e % world == rank:
+                    yw[slot[t, j]] = wts[t, j] * R.feed_forward(x[t:t + 1], *experts[e])[0]
+        gathered = [torch.zeros_like(yw) for _ in range(world)]
+        torch.distributed.all_gather(gathered, yw)  # NVLink peer stores on the GPU; every row has exactly one writer
+        rows = torch.zeros_like(yw)
+        for e in range(E):
+            rows[seg[e]:seg[e + 1]] = gathered[e % world][seg[e]:seg[e + 1]]
+        got = torch.zeros_like(x)
+        for t in range(x.shape[0]):
+            r = rows[slot[t, 0]].clone()
+            for j in range(1, k):
+                r = r + rows[slot[t, j]]  # bf16 add, one rounding per step, ascending expert index
+            got[t] = r
+        exact.append(bool(torch.equal(got, want)))
+        assert all(e % world == rank for e, _ in tiles)
     # key filtering of the sharded model: this rank holds the router, all attention weights and only its own experts
     args = mi.TransformerArgs.from_dict(dict(p))
     m = Transformer(args, expert_parallel=(rank, world)).to(torch.bfloat16)
     m.load_state_dict(sd)
     held = sorted({int(key.split(".")[4]) for key in m.state_dict() if ".experts." in key})
-    q.put((rank, bool(torch.equal(got, want)), float((got.float() - want.float()).abs().max()), held, m._megakernel_ok(1),
+    q.put((rank, exact, held, m._megakernel_ok(1),
            m._owns_key("layers.0.feed_forward.experts.%d.w1.weight" % ((rank + 1) % world)), "layers.0.feed_forward.gate.weight" in m.state_dict()))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -104,7 +125,7 @@ def test_expert_sharded_moe_world2_matches_unsharded_oracle():
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    for rank, equal, worst, held, mega, owns_other, has_gate in res:
-        assert equal, f"rank {rank}: sharded MoE differs from the unsharded oracle by {worst}"  # top-2: bf16(a + b) in any order
+    for rank, exact, held, mega, owns_other, has_gate in res:
+        assert exact == [True, True], f"rank {rank}: gathered-rows MoE differs from the unsharded oracle (top-2, top-3): {exact}"
         assert held == [e for e in range(8) if e % 2 == rank]
-        assert not mega and not owns_other and has_gate  # sharded decode goes through the per-op path with the all-reduce
+        assert not mega and not owns_other and has_gate  # sharded decode: per-layer kernels + the fused exchange, not the megakernel

@@ -1,6 +1,13 @@
-"""Expert-sharded MoE with the real kernels: two processes share cuda:0 (gloo backend, so one GPU is enough),
-each owns the experts e % 2 == rank of a small Mixtral-style model, every MoE layer ends in one all-reduce of [T, dim].
-Prefill + decode logits must equal the unsharded model's bit for bit (top-2 routing: bf16(a + b) in any order)."""
+"""Expert-parallel MoE with the real kernels: each rank owns the experts e % world == rank of a small Mixtral-style
+model; the down projection's epilogue stores every weighted expert row into every rank's row buffer (CUDA-IPC peer memory), a
+flag handshake follows, and every rank combines all rows in the reference's order (csrc/moe.cuh).  Prefill + decode logits must
+equal the UNSHARDED model's bit for bit -- for top-2 and for top-3 routing (no reduction order is left open).
+
+Two set-ups:
+  * two processes sharing cuda:0 (gloo for the handle exchange): one GPU is enough, peer stores go through IPC mappings of the
+    same device; the handshake spins across time slices, so it is slow but exercises the whole protocol;
+  * one process per GPU with NCCL (needs >= 2 GPUs: `gpurun --gpus 2`): peer stores cross NVLink.
+"""
 import os
 import socket
 import sys
@@ -20,18 +27,23 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, q):
+def _worker(rank: int, world: int, port: int, q, backend: str, top_k: int):
     try:
         sys.path.insert(0, str(REPO))
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-        torch.cuda.set_device(0)
-        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+        dev = rank if backend == "nccl" else 0
+        torch.cuda.set_device(dev)
+        if backend == "nccl":
+            torch.distributed.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+        else:
+            torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
         import mistral_inference_b200 as mi
         from mistral_inference_b200 import synth
         from mistral_inference_b200.cache import BufferCache
         from mistral_inference_b200.transformer import Transformer
 
         p = synth.shape("tiny-moe", sliding_window=16)
+        p["moe"] = dict(p["moe"], num_experts_per_tok=top_k)
         sd = synth.synth_state_dict(p, 2, torch.bfloat16, "cuda")
 
         def build(expert_parallel):
@@ -47,13 +59,14 @@ def _worker(rank: int, world: int, port: int, q):
             toks = torch.tensor(synth.synth_prompt(sum(seqlens), p["vocab_size"], 4), device="cuda")
             outs = [m.forward(toks, seqlens, cache)]
             nxt = torch.tensor([5, 7], device="cuda")
-            for _ in range(3):
+            for _ in range(4):  # eager warm-up, graph capture, graph replays
                 lg = m.forward(nxt, [1, 1], cache)
                 outs.append(lg)
                 nxt = lg.argmax(-1)
             return torch.cat(outs).cpu()
 
-        sharded = run(build((rank, world)))  # both ranks run in lock step: the all-reduces pair up
+        sharded = run(build((rank, world)))  # both ranks run in lock step: the handshakes pair up
+        torch.distributed.barrier()
         full = run(build(None)) if rank == 0 else None
         ok = bool(torch.equal(sharded, full)) if rank == 0 else True
         worst = float((sharded - full).abs().max()) if rank == 0 else 0.0
@@ -65,16 +78,28 @@ def _worker(rank: int, world: int, port: int, q):
         raise
 
 
-def test_expert_sharded_forward_equals_unsharded():
+def _run(backend: str, top_k: int):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, backend, top_k)) for r in range(2)]
     for pr in procs:
         pr.start()
-    res = sorted(q.get(timeout=240) for _ in range(2))
+    res = sorted(q.get(timeout=400) for _ in range(2))
     for pr in procs:
         pr.join(timeout=60)
     for rank, ok, worst, err in res:
         assert ok, f"rank {rank}: {err or 'sharded logits differ from the unsharded model by %g' % worst}"
     assert all(pr.exitcode == 0 for pr in procs)
+
+
+@pytest.mark.parametrize("top_k", [2, 3])
+def test_expert_parallel_equals_unsharded_two_processes_one_gpu(top_k):
+    _run("gloo", top_k)
+
+
+@pytest.mark.parametrize("top_k", [2, 3])
+def test_expert_parallel_equals_unsharded_two_gpus_nccl(top_k):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run("nccl", top_k)

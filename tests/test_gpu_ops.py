@@ -493,3 +493,71 @@ def test_decode_attention_vs_flash_attn(ws):
     out = torch.empty(B, H * 128, dtype=torch.bfloat16, device=DEV)
     _abi.attn_decode(q.to(DEV), ck.to(DEV), cv.to(DEV), kv_len.to(DEV), out, H, KV, 128, 4, ws)
     assert_bf16_close(out, ref, max_ulp=2, min_exact=0.5, atol=4e-3, what="attn_decode kernel vs flash_attn")
+
+
+# ----------------------------------------------------------------------------- mixture of experts: device router + grouped experts
+def _moe_case(T, dim, hid, E, seed):
+    x = rnd(T, dim, seed=seed)
+    gate_w = rnd(E, dim, seed=seed + 1, scale=dim ** -0.5)
+    experts = [(rnd(hid, dim, seed=seed + 10 + 3 * e, scale=dim ** -0.5), rnd(dim, hid, seed=seed + 11 + 3 * e, scale=hid ** -0.5),
+                rnd(hid, dim, seed=seed + 12 + 3 * e, scale=dim ** -0.5)) for e in range(E)]
+    return x, gate_w, experts
+
+
+def _router_margin_ulps(x, gate_w, k):
+    logits = F.linear(x, gate_w).float()
+    top = logits.topk(k + 1, dim=-1).values
+    ulp = torch.pow(2.0, torch.floor(torch.log2(top[:, k - 1].abs().clamp_min(1e-30))) - 7)
+    return (top[:, k - 1] - top[:, k]) / ulp
+
+
+@pytest.mark.parametrize("T,dim,hid,k", [(5, 256, 256, 2), (37, 256, 256, 3), (200, 256, 512, 2), (16, 4096, 14336, 2), (300, 4096, 14336, 2)])
+def test_moe_route_grouped_ffn_vs_oracle(T, dim, hid, k):
+    """mb200_moe_route + mb200_moe_grouped_ffn against the oracle's MoE (moe.py:24-32) + residual: routing decisions and weights
+    exactly (tokens whose k-th / (k+1)-th router logits are within 2 ulps excepted), the deterministic row plan exactly, the
+    output within 2 bf16 ulps."""
+    from mistral_inference_b200.moe import MoeBuffers
+
+    from .util import moe_plan_host, moe_route_host
+
+    E = 8
+    x, gate_w, experts = _moe_case(T, dim, hid, E, seed=90)
+    h = rnd(T, dim, seed=89)
+    want = h + R.moe_forward(x, gate_w, experts, k)
+    sel_ref, wts_ref = moe_route_host(x, gate_w, k)
+    safe = _router_margin_ulps(x, gate_w, k) > 2.0
+    ws = _abi.Workspace(_abi.workspace_bytes(max(T, 8), dim, 32, 8, 128, hid, 0, 4), torch.device(DEV))
+    b = MoeBuffers(T, dim, hid, E, k, torch.device(DEV), torch.bfloat16)
+    _abi.moe_route(x.to(DEV), gate_w.to(DEV), E, k, 0, 1, b)
+    torch.cuda.synchronize()
+    sel = b.sel.view(T, k).cpu()
+    assert torch.equal(sel[safe], sel_ref[safe]), "routing differs on tokens without a router near-tie"
+    assert torch.equal(b.wts.view(T, k).cpu()[safe].float(), wts_ref[safe].float()), "routing weights"
+    slot, seg, tiles = moe_plan_host(sel, E, b.tile_rows)
+    plan = b.plan.cpu().tolist()
+    assert torch.equal(b.slot.view(T, k).cpu(), slot), "row plan: slots"
+    assert plan[0] == len(tiles) and plan[1] == seg[-1] and plan[8:8 + E + 1] == seg
+    cap = plan[2]
+    assert [(plan[64 + i], plan[64 + cap + i]) for i in range(len(tiles))] == tiles
+    xs = b.xs.cpu()
+    for t in range(T):
+        for j in range(k):
+            assert torch.equal(xs[slot[t, j]], x[t])
+    import ctypes
+
+    w13 = (ctypes.c_void_p * E)()
+    w2 = (ctypes.c_void_p * E)()
+    keep = []
+    for e, (w1, w2_, w3) in enumerate(experts):
+        packed = torch.stack([w1, w3], 1).reshape(2 * hid, dim).to(DEV)
+        down = w2_.to(DEV)
+        keep += [packed, down]
+        w13[e], w2[e] = packed.data_ptr(), down.data_ptr()
+    out = torch.empty(T, dim, dtype=torch.bfloat16, device=DEV)
+    for _ in range(2):  # twice: stream-K flags and plan buffers must be reusable
+        out.zero_()
+        _abi.moe_grouped_ffn(b, w13, w2, h.to(DEV), out, T, dim, hid, E, k, None, ws)
+        torch.cuda.synchronize()
+        rows = safe & (sel == sel_ref).all(-1)
+        assert rows.float().mean() > 0.8
+        assert_bf16_close(out.cpu()[rows], want[rows], max_ulp=2, min_exact=0.9, atol=2 * 2 ** -8 * want.abs().max().item(), what="moe layer")

@@ -127,3 +127,39 @@ class RouterProbe:
         self._layer_margins = []
         self.calls.append(m)
         return m
+
+
+# ----------------------------------------------------------------------------- MoE row plan (host restatement of csrc/moe.cuh)
+def moe_route_host(x: torch.Tensor, gate_w: torch.Tensor, k: int):
+    """(sel [T, k] ascending expert ids, wts [T, k] bf16) exactly as moe.py:25-27 + the ascending-expert reordering."""
+    import torch.nn.functional as F
+
+    logits = F.linear(x, gate_w)
+    w, sel = torch.topk(logits, k)
+    w = F.softmax(w, dim=1, dtype=torch.float).to(x.dtype)
+    order = sel.argsort(dim=1)
+    return sel.gather(1, order).to(torch.int32), w.gather(1, order)
+
+
+def moe_plan_host(sel: torch.Tensor, E: int, tile_rows: int, shard=(0, 1)):
+    """slot [T, k], segment starts [E + 1], and this rank's (expert, first row) m tiles: pairs keep token order inside an expert's
+    segment, every segment is padded to a multiple of `tile_rows` (the deterministic plan of moe_plan_kernel)."""
+    T, k = sel.shape
+    flat = sel.reshape(-1).tolist()
+    counts = [0] * E
+    for e in flat:
+        counts[e] += 1
+    seg, tiles, rows = [], [], 0
+    for e in range(E):
+        seg.append(rows)
+        m_tiles = -(-counts[e] // tile_rows)
+        if e % shard[1] == shard[0]:
+            tiles += [(e, rows + m * tile_rows) for m in range(m_tiles)]
+        rows += m_tiles * tile_rows
+    seg.append(rows)
+    run = [0] * E
+    slot = []
+    for e in flat:
+        slot.append(seg[e] + run[e])
+        run[e] += 1
+    return torch.tensor(slot, dtype=torch.int32).view(T, k), seg, tiles
