@@ -253,8 +253,13 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
 
 #define MB200_SKINNY_MAX_T 4
 
-/* Workspace contract: the first 64 KiB of `workspace` hold self-resetting counters; the caller zero-fills the
- * workspace ONCE when allocating it (torch.zeros) and never writes to it afterwards. */
+/* Workspace contract: the first 64 KiB of `workspace` hold self-resetting counters (split-KV arrival counts, the decode
+ * kernel's grid-barrier words and epoch, stream-K flags); the caller zero-fills the workspace ONCE when allocating it
+ * (torch.zeros) and never writes to it afterwards.
+ * Concurrency: a workspace carries state BETWEEN and DURING launches, so all calls that share one workspace must be ordered on
+ * one stream (or by events); concurrent streams need one workspace each.  The library keeps no other mutable state that affects
+ * results: process-wide state is limited to the debug hooks below, environment switches read once, and the driver entry point
+ * for tensor-map encoding.  mb200_last_error() is thread-local. */
 #define MB200_WORKSPACE_HEADER_BYTES (64 * 1024)
 
 /* Debug: a device buffer of n_layers*12 uint64 that mb200_decode_step fills with %globaltimer stamps at every phase

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libmb200.so"
+_LIB_PATH = Path(os.environ.get("MB200_LIB_PATH") or Path(__file__).resolve().parent / "libmb200.so")  # override: A/B builds of experiments
 _lib: Optional[ctypes.CDLL] = None
 
 ABI_VERSION = 1

@@ -35,6 +35,18 @@ def _sources_digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines) -> Path:
+    """An extra in-tree library with additional -D flags (A/B experiments: MB200_LIB_PATH selects it at run time)."""
+    out = PKG / f"libmb200_{name}.so"
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(out)] + [str(f) for f in sorted(CSRC.glob("*.cu"))]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed ({proc.returncode})")
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     digest = _sources_digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:

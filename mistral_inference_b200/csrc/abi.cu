@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "attn_decode.cuh"
+#include "attn_decode_tma.cuh"
 #include "attn_prefill.cuh"
 #include "attn_prefill_tcgen05.cuh"
 #include "decode_megakernel.cuh"
@@ -186,6 +187,18 @@ int mb200_attn_decode(const void* q, const void* cache_k, const void* cache_v, c
   }
   const dim3 grid((unsigned)n_splits, (unsigned)n_kv_heads, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
+  const char* which = getenv("MB200_ATTN_DECODE");  // "plain": the register-staged kernel of attn_decode.cuh (A/B comparisons)
+  if (!(which != nullptr && which[0] == 'p')) {
+    if (n_splits > 1) p.counters = (int*)workspace;
+    switch (rep) {
+      case 1: return launch_attn_decode_tma<1>(p, B * W, st);
+      case 2: return launch_attn_decode_tma<2>(p, B * W, st);
+      case 4: return launch_attn_decode_tma<4>(p, B * W, st);
+      case 6: return launch_attn_decode_tma<6>(p, B * W, st);
+      case 8: return launch_attn_decode_tma<8>(p, B * W, st);
+      default: return fail(MB200_E_INVALID, "attn_decode: H/KV=%d unsupported (1,2,4,6,8)", rep);
+    }
+  }
   switch (rep) {
     case 1: attn_decode_kernel<1><<<grid, AD_THREADS, 0, st>>>(p); break;
     case 2: attn_decode_kernel<2><<<grid, AD_THREADS, 0, st>>>(p); break;
@@ -500,12 +513,6 @@ int mb200_decode_step(const mb200_layer_desc* layers_dev, const int32_t* windows
       kvu = e2 ? atoi(e2) : 0;
     }
     p.kv_uncapped = kvu;
-    static int pre = -1;
-    if (pre < 0) {
-      const char* e3 = getenv("MB200_MK_PRELOAD");
-      pre = e3 ? atoi(e3) : 1;
-    }
-    p.preload = pre;
   }
   const size_t smem = (size_t)n_stages * MK_STAGE_BYTES + xs_bytes + tail;
 

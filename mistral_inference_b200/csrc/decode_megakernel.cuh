@@ -36,19 +36,16 @@ constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
 #define MB200_MK_PRODUCERS 2
 #endif
 constexpr int MK_PRODUCER_WARPS = MB200_MK_PRODUCERS;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
-// The producers sit in their own warpgroup (4 warps, the last ones idle) so that setmaxnreg can move registers from it to the two
-// consumer warpgroups: 384 threads launch with 168 registers each (3 warps per SM sub-partition), then the producer warpgroup
-// drops to MK_PRODUCER_REGS and the consumers grow to MK_CONSUMER_REGS.  setmaxnreg.inc can only take what the CTA itself gave
-// back (the SM's unallocated remainder is NOT in the CTA pool -- asking for more blocks forever: the consumers never start and the
-// producers stall on a full ring): (168 - 120) x 128 threads released = (192 - 168) x 256 threads acquired, exactly (the consumers need ~188, the producers ~60).
+#ifndef MB200_MK_WG
+#define MB200_MK_WG 0
+#endif
+#if MB200_MK_WG
+// Experiment (round 2): producers in their own warpgroup so that setmaxnreg can move registers to the consumers (384 threads launch
+// with 168 registers; the pool a CTA can re-acquire is only what it released: (168 - 120) x 128 = (192 - 168) x 256).
 constexpr int MK_THREADS = MK_CONSUMERS + 128;
-#define MK_LAUNCH_REGS 168
-#define MK_PRODUCER_REGS 120
-#define MK_CONSUMER_REGS 192
-static_assert((MK_LAUNCH_REGS - MK_PRODUCER_REGS) * 128 >= (MK_CONSUMER_REGS - MK_LAUNCH_REGS) * MK_CONSUMERS, "setmaxnreg pool");
-#define MK_STR2(x) #x
-#define MK_STR(x) MK_STR2(x)
-static_assert(MB200_MK_PRODUCERS <= 4, "one producer warpgroup");
+#else
+constexpr int MK_THREADS = MK_CONSUMERS + 32 * MK_PRODUCER_WARPS;
+#endif
 constexpr int MK_WEIGHT_STAGE_BYTES = 16 * 1024;   // a weight stage: 2 rows x KC elements x 2 B
 constexpr int MK_MAX_KC = MK_WEIGHT_STAGE_BYTES / 4;  // elements per row chunk
 constexpr int MK_KV_PAD = 16;                      // K/V position rows are laid out with a 16-byte pad (ldmatrix bank spread)
@@ -92,7 +89,6 @@ struct MkParams {
   int n_stages, xs_bytes;
   int inflight_cap;  // max ring stages with outstanding bulk copies (< n_stages)
   int kv_uncapped;
-  int preload;  // 1: consumer warps pull their first stage of the next phase into registers while they wait in a grid barrier
   // scratch (global)
   unsigned* bar_flags;  // grid barrier counter (monotonic, never reset)
   unsigned* bar_epoch;  // device word: number of barriers completed by previous launches (published by the last CTA to finish)
@@ -453,81 +449,22 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
 // `pre(n)` runs on the finishing lane BEFORE the pair's stages are consumed and its result is handed to `epi`: loads the
 // epilogue needs (the residual) are then off the critical path of the phase's last pair (an L2 round trip right before the
 // barrier's release store: measured 3.2-4.2 us barrier latency after wo / down vs 1.75 us after gate/up, which loads nothing).
-//
-// Register extension of the ring (`preload`).  The 12-stage shared-memory ring buffers ~4.4 us of this SM's HBM share; a phase
-// boundary (grid barrier + staging of the next activation vector + arrival skew) that lasts longer stalls the weight stream.
-// Weights do not depend on activations, so the caller ARRIVES at the grid barrier, then calls consume_matrix, which first pulls
-// each warp's first stage of this phase (group 0, chunk 0) out of the ring into registers (16 KB = 128 registers per lane) and
-// releases the slot, and only then runs `between()` -- the barrier wait plus the staging of this phase's input vector.  That is
-// 8 more stages (+2.9 us) of buffering exactly where the bubbles are; the stage sequence itself is unchanged.
-constexpr int MK_PL = MK_MAX_KC / 8 / 32;  // uint4 per row per lane in a full stage (16)
-template <class Between, class Pre, class Epi>
+// `ready(ch)` is called by ALL consumer threads before K-chunk `ch` of the FIRST group is touched: a phase can then stage its
+// input chunk by chunk as the CTAs that produce it finish (pass a no-op when the input was staged up front).
+template <class Ready, class Pre, class Epi>
 __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages, RingState& rs,
-                                               const uint4* xs, int tid, bool preload, Between between, Pre pre, Epi epi) {
+                                               const uint4* xs, int tid, Ready ready, Pre pre, Epi epi) {
   const MatCut c = cut_matrix(N, K);
   const int lane = tid & 31, warp = tid >> 5;
   const int kc8 = c.kc >> 3;  // 16-byte chunks per row chunk
-  uint4 pa[MK_PL], pb[MK_PL];
-  const bool have = preload && warp < min(MK_CONSUMER_WARPS, c.p1 - c.p0);  // warp-uniform
-  {
-    const uint32_t it = rs.it + (uint32_t)warp;
-    const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
-    if (have) {
-      mbar_wait(&empty[slot], par ^ 1, 9, it);  // same guard as below
-      mbar_wait(&full[slot], par, 10, it);
-    }
-    const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
-    const uint4* w1 = w0 + kc8;
-    uint32_t sink = 0u;
-#pragma unroll
-    for (int u = 0; u < MK_PL; ++u) {
-      const int i = lane + 32 * u;
-      pa[u] = pb[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (have && i < kc8) {
-        pa[u] = w0[i];
-        pb[u] = w1[i];
-      }
-      sink |= pa[u].x | pa[u].y | pa[u].z | pa[u].w | pb[u].x | pb[u].y | pb[u].z | pb[u].w;
-    }
-    if (have) {
-      // the slot may only be released once the loads have RETURNED (their values are consumed after the barrier): an
-      // instruction that reads every loaded register has to issue before the arrive does
-      uint32_t dummy;
-      asm volatile("shfl.sync.bfly.b32 %0, %1, 1, 0x1f, 0xffffffff;" : "=r"(dummy) : "r"(sink));
-      __syncwarp();
-      if (lane == 0) mbar_arrive_n(&empty[slot], MK_CONSUMER_WARPS);
-    }
-  }
-  between();
   for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
     const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
     float a0 = 0.f, a1 = 0.f;
     uint2 prefetched = make_uint2(0u, 0u);
     if (warp < g && lane == 0) prefetched = pre(2 * (g0 + warp));
     for (int ch = 0; ch < c.nch; ++ch) {
-      if (have && ch == 0 && g0 == c.p0) {
-        // this stage sits in registers; its slot is already released
-#pragma unroll
-        for (int u = 0; u < MK_PL; ++u) {
-          const int i = lane + 32 * u;
-          if (i < kc8) {
-            uint4 a = pa[u], b = pb[u];
-            // scheduling fence: without it the compiler hoists the bf16 -> fp32 unpacking of all 128 weight registers (256 live
-            // values) to the top of the block and spills; tying this step's inputs to the running sums keeps the steps in order
-            asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w), "+f"(a0), "+f"(a1));
-            const uint4 x = xs[i];
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
-              a0 = fmaf(bf16lo(aw[j]), xl, a0);
-              a0 = fmaf(bf16hi(aw[j]), xh, a0);
-              a1 = fmaf(bf16lo(bw[j]), xl, a1);
-              a1 = fmaf(bf16hi(bw[j]), xh, a1);
-            }
-          }
-        }
-      } else if (warp < g) {
+      if (g0 == c.p0) ready(ch);
+      if (warp < g) {
         const uint32_t it = rs.it + (uint32_t)(ch * g + warp);
         const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
         // Guard (tests/test_megakernel_protocol.py): bulk copies land out of order, so this warp may get here before the
@@ -969,21 +906,25 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
   if (tid >= MK_CONSUMERS) {
     // ================= producers (one thread per producer warp; weights and old K/V rows never wait for activations) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 " MK_STR(MK_PRODUCER_REGS) ";");
-    const int pw = (tid - MK_CONSUMERS) >> 5;
-    if ((tid & 31) == 0 && pw < MK_PRODUCER_WARPS) producer_main(p, ring, full, empty, pw, route, route_bar);
+#if MB200_MK_WG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    if ((tid & 31) == 0 && ((tid - MK_CONSUMERS) >> 5) < MK_PRODUCER_WARPS)
+#else
+    if ((tid & 31) == 0)
+#endif
+      producer_main(p, ring, full, empty, (tid - MK_CONSUMERS) >> 5, route, route_bar);
     return;
   }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 " MK_STR(MK_CONSUMER_REGS) ";");
+#if MB200_MK_WG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+#endif
 
   // ================= consumer warps =================
   // barriers completed by previous launches on this workspace.  Nobody writes the word until every CTA of this launch has
   // finished (see the end of the kernel), and launches are stream ordered, so this read cannot race.
   unsigned epoch = ld_acquire_u32(p.bar_epoch);
+  const unsigned epoch0 = epoch;
   const int64_t token = *p.token;
-  const bool preload = p.preload != 0;
-  // Every weight phase is entered as  grid_arrive(previous phase) ; consume_matrix(..., between = { grid_wait ; stage input })
-  // so that the register preload (see consume_matrix) overlaps the barrier.
   for (int l = 0; l < p.n_layers; ++l) {
     const MkLayer L = p.layers[l];
     const int W = p.windows[l];
@@ -992,21 +933,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
 
     // ---- phase 1: RMSNorm + QKV + RoPE + ring scatter ----
     mk_stamp(p, tid, l, 0);
+    stage_x(xs, x_in, L.attn_norm, p.dim, p.eps, red, tid);
+    mk_stamp(p, tid, l, 1);
     {
       const int slot_row = p.batch_row * W + p.pos % W;
       const float* rope_row = p.rope + (int64_t)p.pos * (kHeadDim / 2) * 2;
       bf16* ck = L.cache_k + (int64_t)slot_row * kv_dim;
       bf16* cv = L.cache_v + (int64_t)slot_row * kv_dim;
-      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       if (l > 0) {  // the barrier that ends the previous layer
-                         grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                         bar_stamp(p, tid, l - 1, 5, 1);
-                         mk_stamp(p, tid, l - 1, 11);
-                       }
-                       stage_x(xs, x_in, L.attn_norm, p.dim, p.eps, red, tid);
-                       mk_stamp(p, tid, l, 1);
-                     },
+      consume_matrix(q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {},
                      [&](int n) { return *reinterpret_cast<const uint2*>(rope_row + ((n & (kHeadDim - 1)) >> 1) * 2); },
                      [&](int n, float a0, float a1, uint2 pf) {
         const float y0 = round_bf16(a0), y1 = round_bf16(a1);
@@ -1038,68 +972,48 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     mk_stamp(p, tid, l, 13);
     mk_attention_combine(p, W, tid, reinterpret_cast<float*>(xs));
     mk_stamp(p, tid, l, 4);
-    grid_arrive(p, tid, epoch, l, 2);
+    grid_barrier(p, tid, epoch, l, 2);
+    mk_stamp(p, tid, l, 5);
 
     // ---- phase 3: wo + residual ----
-    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                   [&]() {
-                     grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                     bar_stamp(p, tid, l, 2, 1);
-                     mk_stamp(p, tid, l, 5);
-                     stage_x(xs, p.abuf, nullptr, q_dim, 0.f, red, tid);
-                   },
-                   [&](int n) { return make_uint2(ldcg_u32(x_in + n), 0u); },
-                   [&](int n, float a0, float a1, uint2 pf) {
-                     const uint32_t r = pf.x;
-                     *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
-                   });
+    stage_x(xs, p.abuf, nullptr, q_dim, 0.f, red, tid);
+    consume_matrix(p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(x_in + n), 0u); }, [&](int n, float a0, float a1, uint2 pf) {
+      const uint32_t r = pf.x;
+      *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
+    });
     mk_stamp(p, tid, l, 6);
-    grid_arrive(p, tid, epoch, l, 3);
+    grid_barrier(p, tid, epoch, l, 3);
+    mk_stamp(p, tid, l, 7);
 
     if (p.n_experts == 0) {
-      // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
-      consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                       bar_stamp(p, tid, l, 3, 1);
-                       mk_stamp(p, tid, l, 7);
-                       stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-                     },
-                     [&](int) { return make_uint2(0u, 0u); },
-                     [&](int n, float a0, float a1, uint2) {
-                       const float s = round_bf16(ref_silu(round_bf16(a0)));
-                       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
-                     });
+    // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
+      stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
+      consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); }, [&](int n, float a0, float a1, uint2) {
+        const float s = round_bf16(ref_silu(round_bf16(a0)));
+        p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
+      });
       mk_stamp(p, tid, l, 8);
-      grid_arrive(p, tid, epoch, l, 4);
+      grid_barrier(p, tid, epoch, l, 4);
+      mk_stamp(p, tid, l, 9);
 
       // ---- phase 5: down + residual ----
       // (Tried: no full barrier here -- stage g chunk by chunk as the barrier words of the CTA range that produced each K-chunk
-      //  complete.  Correct, but 4 polling rounds + 4 block syncs cost more than the ~5 us gate/up arrival skew they hide.)
-      consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                       bar_stamp(p, tid, l, 4, 1);
-                       mk_stamp(p, tid, l, 9);
-                       stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
-                     },
-                     [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
+      //  complete, via grid_arrive / grid_wait + the `ready` hook.  Correct, but 4 polling rounds + 4 block syncs cost more than
+      //  the ~5 us gate/up arrival skew they hide: 345 vs 351 tok/s.)
+      stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
+      consume_matrix(p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
                      [&](int n, float a0, float a1, uint2 pf) {
                        const uint32_t r = pf.x;
                        *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
                      });
     } else {
       // ---- phase 4 (MoE): RMSNorm + router; gate/up + SiLU*mul of the selected experts (ascending expert index) ----
-      // (no register preload: the expert weight stream itself waits for the routing decision)
-      grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-      bar_stamp(p, tid, l, 3, 1);
-      mk_stamp(p, tid, l, 7);
       stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
       moe_route(p, l, xs, red, route, route_bar, tid);
       const MoeRoute rt = *route;
       for (int j = 0; j < p.top_k; ++j) {
         bf16* gj = p.gbuf + (size_t)j * p.hidden;
-        consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, false, [&]() {}, [&](int) { return make_uint2(0u, 0u); },
+        consume_matrix(2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); },
                        [&](int n, float a0, float a1, uint2) {
                          const float sv = round_bf16(ref_silu(round_bf16(a0)));
                          gj[n >> 1] = __float2bfloat16_rn(sv * round_bf16(a1));
@@ -1116,10 +1030,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
                        });
     }
     mk_stamp(p, tid, l, 10);
-    grid_arrive(p, tid, epoch, l, 5);  // waited for at the top of the next layer (or before the lm head)
+    grid_barrier(p, tid, epoch, l, 5);
+    mk_stamp(p, tid, l, 11);
   }
 
   // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) + greedy argmax ----
+  stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
   // argmax key: order-preserving map of the fp32 logit in the high word, ~index in the low word, so that the maximum key is
   // the largest logit and, among equal logits, the SMALLEST index (what torch.argmax returns; generate.py:156)
   unsigned long long best = 0ull;
@@ -1128,16 +1044,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     return ((unsigned long long)u << 32) | (unsigned)(0x7fffffff - idx);
   };
-  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                 [&]() {
-                   if (p.n_layers > 0) {
-                     grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                     bar_stamp(p, tid, p.n_layers - 1, 5, 1);
-                     mk_stamp(p, tid, p.n_layers - 1, 11);
-                   }
-                   stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
-                 },
-                 [&](int) { return make_uint2(0u, 0u); },
+  consume_matrix(p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, [&](int) {}, [&](int) { return make_uint2(0u, 0u); },
                  [&](int n, float a0, float a1, uint2) {
                    const float y0 = round_bf16(a0), y1 = round_bf16(a1);
                    *reinterpret_cast<float2*>(p.logits + n) = make_float2(y0, y1);
@@ -1176,6 +1083,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
       st_release_u32(p.bar_epoch, epoch);
     }
   }
+  (void)epoch0;
 }
 
 }  // namespace mb200

@@ -21,6 +21,22 @@ from .rope import precompute_freqs_cis
 from .transformer_layers import RMSNorm, TransformerBlock
 
 ROPE_TABLE_LEN = 128_000  # transformer.py:116
+_NVTX = os.environ.get("MB200_NVTX", "0") == "1"
+
+
+class _nvtx:
+    """NVTX range around a phase of the forward (MB200_NVTX=1; visible in nsys / ncu --nvtx): the layer loop, the decode step."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
 
 class _OutputView:
@@ -209,9 +225,10 @@ class Transformer(nn.Module):
         assert self.tok_embeddings is not None
         h = self.tok_embeddings(input_ids)
         rope = self.rope_table
-        for local_layer_id, layer in enumerate(self.layers.values()):
-            view = cache.get_view(local_layer_id, input_metadata[local_layer_id]) if cache is not None else None
-            h = layer(h, rope, positions, view, ws)
+        with _nvtx(f"mb200.layers[T={num_toks}]"):
+            for local_layer_id, layer in enumerate(self.layers.values()):
+                view = cache.get_view(local_layer_id, input_metadata[local_layer_id]) if cache is not None else None
+                h = layer(h, rope, positions, view, ws)
         return h
 
     def _check_positions(self, cache: BufferCache, seqlens: List[int]) -> None:
@@ -293,9 +310,10 @@ class Transformer(nn.Module):
             st["token"].copy_(tok, non_blocking=True)
             tok = st["token"]
         self.last_argmax = st["next"]
-        _abi.decode_step(st["layers"], st["windows"], self.n_local_layers, self.tok_embeddings.weight, self.norm.weight, self.output_weight,
-                         self.rope_table, tok, pos, 0, st["logits"], st["next"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
-                         self.vocab_size, a.norm_eps, ws, st["E"], st["k"], st["moe_gate"], st["moe_w13"], st["moe_w2"])
+        with _nvtx("mb200.decode_megakernel"):
+            _abi.decode_step(st["layers"], st["windows"], self.n_local_layers, self.tok_embeddings.weight, self.norm.weight, self.output_weight,
+                             self.rope_table, tok, pos, 0, st["logits"], st["next"], a.dim, a.hidden_dim, a.n_heads, a.n_kv_heads, a.head_dim,
+                             self.vocab_size, a.norm_eps, ws, st["E"], st["k"], st["moe_gate"], st["moe_w13"], st["moe_w2"])
         cache.update_seqlens([1])
         self._last_static_logits = st["logits"].data_ptr()
         return st["logits"]
