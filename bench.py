@@ -53,14 +53,17 @@ def experts_touched(E: int, k: int, batch: int) -> float:
     return E * (1.0 - (1.0 - k / E) ** batch) if batch > 1 else float(k)
 
 
-def decode_bytes_per_step(p: dict, kv_len: float, batch: int = 1) -> int:
-    """weights read once + KV rows of the visible window, bf16."""
+def decode_bytes_per_step(p: dict, kv_len: float, batch: int = 1, touched: float = None) -> int:
+    """weights read once + KV rows of the visible window, bf16.  MoE: `touched` = measured number of
+    distinct experts a layer streams per step (default: the expectation under uniform routing)."""
     dim, hd, hid, H, KV, V, L = p["dim"], p["head_dim"], p["hidden_dim"], p["n_heads"], p["n_kv_heads"], p["vocab_size"], p["n_layers"]
     p_attn = 2 * dim * H * hd + 2 * dim * KV * hd
     p_ffn = 3 * dim * hid
     moe = p.get("moe") or {}
     if moe:  # the router matrix + only the experts some token selected are read (moe.py:24-32)
-        p_ffn = experts_touched(moe["num_experts"], moe["num_experts_per_tok"], batch) * p_ffn + moe["num_experts"] * dim
+        if touched is None:
+            touched = experts_touched(moe["num_experts"], moe["num_experts_per_tok"], batch)
+        p_ffn = touched * p_ffn + moe["num_experts"] * dim
     weights = 2 * (L * (p_attn + p_ffn + 2 * dim) + V * dim + dim)
     kv = 2 * L * batch * 2 * kv_len * KV * hd
     return int(weights + kv)
@@ -149,6 +152,17 @@ def build_gpu_model(p: dict, max_batch: int, seed: int = 0, expert_parallel=None
             if model._owns_key(k):
                 model._assign(k, synth.synth_tensor(k, shp, seed, torch.bfloat16, dev))
     return model.eval()
+
+
+def moe_stats(model, batch: int):
+    """(sum of distinct experts over MoE calls, calls) accumulated by moe_plan_kernel in the decode-sized row buffers."""
+    ws = getattr(model, "_ws", None)
+    tot = calls = 0
+    for key, b in (ws._moe.items() if ws is not None else []):
+        if key[0] == batch:
+            h = b.plan[:8].tolist()
+            tot, calls = tot + h[4], calls + h[5]
+    return tot, calls
 
 
 def timed_decode(model, cache, tok, steps: int, warmup: int, world: int, dev_index: int, sample_clocks: bool = True):
@@ -248,7 +262,8 @@ def run_ours(a, rank: int, world: int):
     def fresh_cache():
         return BufferCache(L, a.batch, max_seq, p["n_kv_heads"], p["head_dim"], p.get("sliding_window")).to(model.device, model.dtype)
 
-    prompt = torch.tensor(synth.synth_prompt(a.prefill, p["vocab_size"], 7) * a.batch, device=model.device)
+    # a different prompt per sequence (identical sequences would route identically: a batch of 8 would touch 2 experts, not ~7)
+    prompt = torch.tensor(sum((synth.synth_prompt(a.prefill, p["vocab_size"], 7 + 13 * b) for b in range(a.batch)), []), device=model.device)
     seqlens = [a.prefill] * a.batch
 
     if os.environ.get("MB200_PROFILE") == "1":  # ncu --profile-from-start off: skip the synthetic-weight generation
@@ -278,17 +293,18 @@ def run_ours(a, rank: int, world: int):
         tok = last.argmax(-1)
         del last
     prefill_ms = max_over_ranks(sorted(times)[1], world, model.device)
-    pf = prefill_flops(p, a.prefill) * a.batch
-    if not full_logits:
-        pf -= 2.0 * (a.prefill - 1) * a.batch * p["vocab_size"] * p["dim"]  # the lm head ran on the last rows only
+    pf = prefill_flops(p, a.prefill) * a.batch  # the lm head runs on every row in both variants (forward_logprobs: block by block)
 
     # ---- decode: device-resident loop (value) ----
     megakernel = model._megakernel_ok(a.batch)
+    st0 = moe_stats(model, a.batch)
     dec_ms, kern_us, clocks, tok = timed_decode(model, cache, tok, a.steps, a.warmup, world, dev_index)
+    st1 = moe_stats(model, a.batch)
+    touched = (st1[0] - st0[0]) / (st1[1] - st0[1]) if st1[1] > st0[1] else None  # measured distinct experts per MoE layer call
     ms_per_step = dec_ms / a.steps
     value = whole_job_tokens_per_s(replicas, a.batch, a.steps, dec_ms)
     kv_len = min(W, a.prefill + max(a.warmup, 3) + a.steps / 2.0)
-    step_bytes = decode_bytes_per_step(p, kv_len, a.batch)
+    step_bytes = decode_bytes_per_step(p, kv_len, a.batch, touched)
     peaks = measured_peaks()
     n_gpus_bw = world if expert else 1
 
@@ -358,7 +374,9 @@ def run_ours(a, rank: int, world: int):
     roof = {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": bw_peak, "unit": "GB/s", "frac": round(achieved / bw_peak, 4),
             "traffic": traffic, "bytes_per_launch": step_bytes, "us_per_launch": round(kern_us, 2), "peak_source": peaks["source"], "timing": timing}
     if p.get("moe") and a.batch > 1:
-        roof["note"] = "MoE bytes use the expected number of distinct experts per layer under uniform routing"
+        roof["distinct_experts_per_layer"] = round(touched, 3) if touched is not None else None
+        roof["note"] = ("MoE bytes use the MEASURED number of distinct experts per layer and step (device-side counter of the routing plan)" if touched is not None
+                        else "MoE bytes use the expected number of distinct experts per layer under uniform routing")
 
     cpu = cpu_baseline(a, p, bounded_seconds=20.0) if (world == 1 and not a.no_cpu_baseline) else None
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
@@ -387,7 +405,7 @@ def run_ours(a, rank: int, world: int):
                           "unit": "GB/s", "frac": round(step_gbs / bw_peak, 4), "peak_source": peaks["source"]},
         "prefill": {"tokens": a.prefill * a.batch, "ms": round(prefill_ms, 2), "tflops": round(pf / prefill_ms / 1e9, 1),
                     "frac_of_burst_peak": round(pf / prefill_ms / 1e9 / (peaks["bf16_tflops"] * n_gpus_bw), 4), "algorithmic_flops": pf,
-                    "lm_head": "all rows" if full_logits else "last row per sequence only (the full [T, V] fp32 logits would not fit)",
+                    "lm_head": "all rows, [T, V] fp32 logits materialised" if full_logits else "all rows, block by block with the fused log-softmax + gather (the full [T, V] fp32 logits would not fit)",
                     "bound": "tensor", "peak_tflops": peaks["bf16_tflops"] * n_gpus_bw, "kernels": prefill_kernels},
         "parity": parity,
         "sharded": sharded,
@@ -407,7 +425,7 @@ def run_sharded(a, rank: int, world: int, dev_index: int):
     model = build_gpu_model(p, B, expert_parallel=(rank, world))
     K, Wm = min(a.steps, 32), max(a.warmup, 3)
     cache = BufferCache(p["n_layers"], B, P + 2 * (K + Wm) + 16, p["n_kv_heads"], p["head_dim"], None).to(model.device, model.dtype)
-    prompt = torch.tensor(synth.synth_prompt(P, p["vocab_size"], 11) * B, device=model.device)
+    prompt = torch.tensor(sum((synth.synth_prompt(P, p["vocab_size"], 11 + 13 * b) for b in range(B)), []), device=model.device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -416,13 +434,21 @@ def run_sharded(a, rank: int, world: int, dev_index: int):
     torch.cuda.synchronize()
     prefill_ms = max_over_ranks(e0.elapsed_time(e1), world, model.device)
     tok = last.argmax(-1)
+    st0 = moe_stats(model, B)
     ms, kern_us, _, _ = timed_decode(model, cache, tok, K, Wm, world, dev_index, sample_clocks=False)
+    st1 = moe_stats(model, B)
+    touched = (st1[0] - st0[0]) / (st1[1] - st0[1]) if st1[1] > st0[1] else None
     peaks = measured_peaks()
-    step_bytes = decode_bytes_per_step(p, P + Wm + K / 2.0, B)
+    step_bytes = decode_bytes_per_step(p, P + Wm + K / 2.0, B, touched)
     gbs = step_bytes / (ms / K * 1e-3) / 1e9
-    comm = getattr(model, "comm_stats", lambda: None)()
+    moe = p["moe"]
+    rows = B * moe["num_experts_per_tok"]
+    comm = {"kind": "all-gather of the weighted expert output rows, written by the down-projection GEMM's epilogue straight into every rank's row "
+                    "buffer (NVLink peer stores, CUDA-IPC mappings) + one flag handshake per MoE layer; no reduction, no NCCL call on the data path",
+            "rows_per_layer": rows, "bytes_pushed_per_rank_per_layer": int(rows / world * (world - 1) * p["dim"] * 2), "moe_layers_per_step": p["n_layers"]}
     return {"workload": f"{name} expert-sharded over {world} GPUs, batch {B}, {P}-token prefill then decode", "tokens_per_s": round(B * K * 1000.0 / ms, 1),
             "ms_per_step": round(ms / K, 3), "steps": K, "prefill_ms": round(prefill_ms, 1), "algorithmic_bytes_per_step": step_bytes,
+            "distinct_experts_per_layer": round(touched, 3) if touched is not None else None,
             "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"] * world, "unit": "GB/s", "frac": round(gbs / (peaks["hbm_gbs"] * world), 4)},
             "exchange": comm}
 

@@ -27,8 +27,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int run_rmsnorm(const void* x, const void* w, void* out, int64_t T, int64_t dim, float eps, cudaStream_t st) {
   MB_CHECK_ARG(dim % 8 == 0 && T >= 0, "rmsnorm: dim=%lld must be a multiple of 8", (long long)dim);
   if (T == 0) return MB200_OK;
-  rmsnorm_kernel<<<(unsigned)T, 256, 0, st>>>((const uint4*)x, (const uint4*)w, (uint4*)out, (int)dim, eps);
-  MB_CHECK_LAUNCH("rmsnorm_kernel");
+  MB_CHECK_CUDA(launch_pdl(rmsnorm_kernel, dim3((unsigned)T), dim3(256), 0, st, (const uint4*)x, (const uint4*)w, (uint4*)out, (int)dim, eps));
   return MB200_OK;
 }
 

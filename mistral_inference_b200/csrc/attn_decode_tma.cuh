@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(ADT_THREADS, 2)
 
   const int s = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();  // q, the ring rows of this step and kv_len come from the preceding kernels
   const int len = p.kv_len[b];
   const int C = (len + p.S - 1) / p.S;
   const int k_begin = min(s * C, len), k_end = min(k_begin + C, len);
@@ -277,8 +279,7 @@ int launch_attn_decode_tma(const AttnDecodeParams& p, int64_t max_batch_rows, cu
   if (rc) return rc;
   MB_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_tma_kernel<REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ADT_SMEM));
   const dim3 grid((unsigned)p.S, (unsigned)p.KV, (unsigned)p.B);
-  attn_decode_tma_kernel<REP><<<grid, ADT_THREADS, ADT_SMEM, st>>>(map_k, map_v, p);
-  MB_CHECK_LAUNCH("attn_decode_tma_kernel");
+  MB_CHECK_CUDA(launch_pdl(attn_decode_tma_kernel<REP>, grid, dim3(ADT_THREADS), (size_t)ADT_SMEM, st, map_k, map_v, p));
   return MB200_OK;
 }
 

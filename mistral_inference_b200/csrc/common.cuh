@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/mistral_b200.h"
 
@@ -85,5 +86,41 @@ __device__ __forceinline__ void ref_cmul(float a, float b, float c, float d, flo
 }
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------------
+// The decode step of a batch is ~7 short kernels per layer, each preceded by launch latency and a pipeline fill and followed by
+// a drain: measured 10-20 us of fixed cost per weight-streaming GEMM at Nemo-12B shapes, a third of the step.  Kernels launched
+// through launch_pdl() may start while their predecessor in the stream is still running: everything up to pdl_wait() -- barrier
+// init, TMEM allocation, tensor-map prefetch and, in the GEMMs, the first ring of WEIGHT tiles, which no kernel ever writes --
+// overlaps the predecessor's tail.  pdl_wait() returns once the predecessor grid has completed and its writes are visible (and,
+// transitively, everything before it).  A kernel signals with pdl_trigger() that its dependents may be scheduled; the hardware
+// launches them only when EVERY CTA of this grid has triggered or exited, i.e. when this grid no longer needs SM resources.
+// Both are no-ops in a kernel launched the ordinary way.  MB200_PDL=0 launches everything the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB200_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace mb200

@@ -7,6 +7,8 @@ namespace mb200 {
 // out = bf16( bf16( x * rsqrt(mean(x^2) + eps) ) * w ), one CTA per token (transformer_layers.py:115-120)
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, uint4* __restrict__ out,
                                                       int dim, float eps) {
+  pdl_trigger();
+  pdl_wait();  // x is the previous kernel's output
   const int kc = dim >> 3;
   const uint4* xr = x + (int64_t)blockIdx.x * kc;
   uint4* orow = out + (int64_t)blockIdx.x * kc;

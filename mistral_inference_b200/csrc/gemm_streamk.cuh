@@ -50,6 +50,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  if (GROUPED) pdl_wait();  // the routing plan (m tiles) is the preceding kernels' output
   const int num_m = GROUPED ? plan[0] : 1, num_n = p.N / SK_BN, num_k = p.K / TG_BK;
   const int32_t* tile_expert = GROUPED ? plan + MOE_PLAN_HEADER : nullptr;
   const int32_t* tile_row0 = GROUPED ? plan + MOE_PLAN_HEADER + plan[2] : nullptr;
@@ -76,25 +77,39 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer =================
+    // Iteration `it` handles unit u_begin + it.  Weights are never written by any kernel: the W tiles of the first ring are
+    // requested BEFORE the programmatic-dependent-launch wait (they stream in while the previous kernel drains); the A tiles of
+    // those stages, which the previous kernel produced, follow after it.
     if (lane == 0) {
-      uint32_t it = 0;
-      for (long long u = u_begin; u < u_end;) {
-        const int tile = (int)(u / num_k), kb0 = (int)(u % num_k);
-        const int kb1 = (int)min((long long)num_k, kb0 + (u_end - u));
-        const int m0 = GROUPED ? tile_row0[tile % num_m] : 0, n0 = (tile / num_m) * SK_BN;
-        const CUtensorMap* wmap = GROUPED ? map_w_base + tile_expert[tile % num_m] : map_w_base;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
-          mbar_wait(&empty[s], par ^ 1, 21, it);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, m0);
+      const uint32_t n_it = (uint32_t)(u_end - u_begin);
+      auto issue = [&](uint32_t it, bool do_a, bool do_w) {
+        const uint32_t u = (uint32_t)u_begin + it;
+        const int tile = (int)(u / (uint32_t)num_k), kb = (int)(u % (uint32_t)num_k);
+        const uint32_t s = it % STAGES;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        if (do_w) {
+          const int n0 = (tile / num_m) * SK_BN;
+          const CUtensorMap* wmap = GROUPED ? map_w_base + tile_expert[tile % num_m] : map_w_base;
           tma_load_2d(sa + A_BYTES, wmap, &full[s], kb * TG_BK, n0);
         }
-        u += kb1 - kb0;
+        if (do_a) tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, GROUPED ? tile_row0[tile % num_m] : 0);
+      };
+      const uint32_t head = GROUPED ? 0u : (n_it < (uint32_t)STAGES ? n_it : (uint32_t)STAGES);  // (grouped: the tile list itself is the previous kernel's output)
+      for (uint32_t it = 0; it < head; ++it) {
+        mbar_arrive_expect_tx(&full[it % STAGES], STAGE_BYTES);  // first lap: every slot is free
+        issue(it, false, true);
+      }
+      pdl_wait();
+      for (uint32_t it = 0; it < head; ++it) issue(it, true, false);
+      for (uint32_t it = head; it < n_it; ++it) {
+        const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+        mbar_wait(&empty[s], par ^ 1, 21, it);
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        issue(it, true, true);
       }
     }
   } else if (warp == 1) {
@@ -125,6 +140,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
   } else {
     // ================= epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. + 31 =================
     const int lane_base = (warp & 3) * 32;
+    if (!GROUPED) pdl_wait();  // stores below must not pass the predecessor's reads of the same buffers (returns at once when it is done)
     const bool row_ok = TA == 128 || lane_base + lane < TA;  // accumulator rows >= TA come from beyond the short A box
     const int etid = (int)threadIdx.x - 64;                  // 0..127 among the epilogue threads
     uint32_t seg = 0;
@@ -253,8 +269,7 @@ int launch_streamk_ta(const GemmParams& g, void* workspace, size_t workspace_byt
   const long long units = (long long)(g.N / SK_BN) * (g.K / TG_BK);
   const int grid = (int)(units < sms ? units : sms);
   MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_streamk_kernel<MODE, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-  gemm_streamk_kernel<MODE, TA><<<grid, TG_THREADS, Cfg::kSmem, stream>>>(map_a, map_w, p);
-  MB_CHECK_LAUNCH("gemm_streamk_kernel");
+  MB_CHECK_CUDA(launch_pdl(gemm_streamk_kernel<MODE, TA>, dim3((unsigned)grid), dim3(TG_THREADS), (size_t)Cfg::kSmem, stream, map_a, map_w, p));
   return MB200_OK;
 }
 

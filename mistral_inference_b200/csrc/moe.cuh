@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) moe_route_kernel(const bf16* __restrict__
 }
 
 // ---- plan: one CTA ---------------------------------------------------------------------------------------------------------
-// plan layout (int32): [0] m tiles owned by this rank, [1] padded rows in total, [2] tile capacity, [3] pairs, [8 + e] start of
+// plan layout (int32): [0] m tiles owned by this rank, [1] padded rows in total, [2] tile capacity, [3] pairs, [4]/[5] statistics, [8 + e] start of
 // expert e's segment (e = 0..E), then tile_expert[capacity], tile_row0[capacity] from word MOE_PLAN_HEADER.
 constexpr int MP_THREADS = 1024;
 __global__ void __launch_bounds__(MP_THREADS) moe_plan_kernel(const int32_t* __restrict__ sel, int pairs, int E, int tile_rows, int shard_rank,
@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(MP_THREADS) moe_plan_kernel(const int32_t* __r
     plan[1] = rows;
     plan[2] = tile_cap;
     plan[3] = pairs;
+    int touched = 0;
+    for (int e = 0; e < E; ++e) touched += total[e] > 0;
+    plan[4] += touched;  // statistics (never reset by the kernel): experts with at least one row, summed over calls ...
+    plan[5] += 1;        // ... and the number of calls: the measured "distinct experts per layer" of bench.py
   }
   __syncthreads();
   int run[MOE_MAX_EXPERTS];
@@ -336,8 +340,7 @@ int launch_grouped_streamk(const void* a, int64_t rows_cap, int64_t K, int64_t N
   p.partials = reinterpret_cast<float*>((uint8_t*)workspace + header);
   p.flags = reinterpret_cast<unsigned*>((uint8_t*)workspace + SK_FLAGS_OFFSET);
   MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_streamk_grouped_kernel<MODE, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-  gemm_streamk_grouped_kernel<MODE, TA><<<sms, TG_THREADS, Cfg::kSmem, stream>>>(map_a, maps, p, plan);
-  MB_CHECK_LAUNCH("gemm_streamk_grouped_kernel");
+  MB_CHECK_CUDA(launch_pdl(gemm_streamk_grouped_kernel<MODE, TA>, dim3((unsigned)sms), dim3(TG_THREADS), (size_t)Cfg::kSmem, stream, map_a, maps, p, plan));
   return MB200_OK;
 }
 
