@@ -321,14 +321,23 @@ int mb200_moe_route(const void* hn, const void* gate_w, int64_t T, int64_t dim, 
   MB_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "moe_route: shard %lld of %lld", (long long)shard_rank,
                (long long)shard_world);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)ceil_div(T, 8);
+  const bool wide = T <= 256;  // decode-sized batches: one CTA per token
+  const dim3 blocks(wide ? (unsigned)T : (unsigned)ceil_div(T, 8));
+#define MB_ROUTE(EE)                                                                                                                              \
+  if (wide)                                                                                                                                       \
+    MB_CHECK_CUDA(launch_pdl(moe_route_kernel<EE, true>, blocks, dim3(256), 0, st, (const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim,      \
+                             (int)top_k, sel, (bf16*)wts));                                                                                       \
+  else                                                                                                                                            \
+    MB_CHECK_CUDA(launch_pdl(moe_route_kernel<EE, false>, blocks, dim3(256), 0, st, (const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim,     \
+                             (int)top_k, sel, (bf16*)wts));
   switch (n_experts) {
-    case 2: moe_route_kernel<2><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
-    case 4: moe_route_kernel<4><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
-    case 8: moe_route_kernel<8><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
-    case 16: moe_route_kernel<16><<<blocks, 256, 0, st>>>((const bf16*)hn, (const bf16*)gate_w, (int)T, (int)dim, (int)top_k, sel, (bf16*)wts); break;
+    case 2: MB_ROUTE(2) break;
+    case 4: MB_ROUTE(4) break;
+    case 8: MB_ROUTE(8) break;
+    case 16: MB_ROUTE(16) break;
     default: return fail(MB200_E_INVALID, "moe_route: n_experts=%lld unsupported (2, 4, 8, 16)", (long long)n_experts);
   }
+#undef MB_ROUTE
   MB_CHECK_LAUNCH("moe_route_kernel");
   const int tile_rows = moe_tile_rows(T);
   const int64_t pairs = T * top_k, cap = moe_tile_cap(pairs, n_experts, tile_rows);

@@ -45,7 +45,13 @@ struct TgCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlack = TA < 128 ? TG_A_BYTES : 0;  // the last stage's M = 128 read must stay inside the allocation
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - kSlack) / kStageBytes;
-  static constexpr int kStages = (TA < 128 || BN < 128) ? (kMaxStages > 24 ? 24 : kMaxStages) : (BN == 128 ? 6 : 4);
+  // decode-sized variants: the ring is capped at ~100 KB so that TWO CTAs fit one SM -- not two of the same launch (a launch has
+  // one CTA per SM) but the tail of one kernel and the head of the next: under programmatic dependent launch the successor's CTA
+  // moves in beside the running one, requests its first ring of weight tiles and waits; 80 KB in flight per CTA is still above
+  // the ~45-65 KB bandwidth-delay product of one SM's HBM share.
+  static constexpr int kCoResidentStages = (100 * 1024) / kStageBytes;
+  static constexpr int kStages = (TA < 128 || BN < 128) ? (kCoResidentStages < 3 ? 3 : (kCoResidentStages > kMaxStages ? kMaxStages : kCoResidentStages))
+                                                        : (BN == 128 ? 6 : 4);
   static constexpr int kSmem = kStages * kStageBytes + kSlack + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // 2 accumulators
   // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24

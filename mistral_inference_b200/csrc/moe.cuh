@@ -25,19 +25,23 @@ namespace mb200 {
 
 constexpr int MOE_MAX_TOPK = 8;
 
-// ---- router: one warp per token --------------------------------------------------------------------------------------------
-template <int E>
+// ---- router: one warp per token (WIDE = false: prefill) or one CTA per token with the 8 warps splitting the row (WIDE = true:
+// decode-sized batches, where a single warp walking 4096 dims x 8 experts is pure load latency: 36 us measured for 8 tokens) ------
+template <int E, bool WIDE>
 __global__ void __launch_bounds__(256) moe_route_kernel(const bf16* __restrict__ hn, const bf16* __restrict__ gate_w, int T, int dim, int k,
                                                         int32_t* __restrict__ sel, bf16* __restrict__ wts) {
+  pdl_trigger();
+  pdl_wait();  // hn is the preceding RMSNorm's output
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * 8 + warp;
+  const int t = WIDE ? (int)blockIdx.x : (int)blockIdx.x * 8 + warp;
   if (t >= T) return;
   const int kc = dim >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(hn + (int64_t)t * dim);
   float acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
-  for (int c = lane; c < kc; c += 32) {
+#pragma unroll 2
+  for (int c = WIDE ? (int)threadIdx.x : lane; c < kc; c += WIDE ? 256 : 32) {
     const uint4 xv = xr[c];
     const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -51,8 +55,26 @@ __global__ void __launch_bounds__(256) moe_route_kernel(const bf16* __restrict__
       }
     }
   }
+  if constexpr (WIDE) {  // fold the 8 warps' partial sums in a fixed order
+    __shared__ float part[8][E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) acc[e] = round_bf16(warp_sum(acc[e]));  // the router Linear's bf16 output (moe.py:25)
+    for (int e = 0; e < E; ++e) {
+      const float v = warp_sum(acc[e]);
+      if (lane == 0) part[warp][e] = v;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][e];
+      acc[e] = round_bf16(v);  // the router Linear's bf16 output (moe.py:25)
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = round_bf16(warp_sum(acc[e]));  // the router Linear's bf16 output (moe.py:25)
+  }
   if (lane != 0) return;
   int se[MOE_MAX_TOPK];
   float sv[MOE_MAX_TOPK];
@@ -102,6 +124,41 @@ __global__ void __launch_bounds__(MP_THREADS) moe_plan_kernel(const int32_t* __r
   int32_t* seg = sm + E * MP_THREADS;
   int32_t* total = seg + E + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (pairs <= 512) {
+    // decode-sized batch: thread e walks the whole (short) pair list for expert e -- same deterministic plan, a few hundred cycles
+    if (tid < E) {
+      int n = 0;
+      for (int i = 0; i < pairs; ++i)
+        if (sel[i] == tid) slot[i] = n++;  // position inside the expert's segment; the segment start is added below
+      total[tid] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rows = 0, n = 0, touched = 0;
+      for (int e = 0; e < E; ++e) {
+        seg[e] = rows;
+        plan[8 + e] = rows;
+        const int m_tiles = (total[e] + tile_rows - 1) / tile_rows;
+        touched += total[e] > 0;
+        if (e % shard_world == shard_rank)
+          for (int m = 0; m < m_tiles && n < tile_cap; ++m, ++n) {
+            plan[MOE_PLAN_HEADER + n] = e;
+            plan[MOE_PLAN_HEADER + tile_cap + n] = rows + m * tile_rows;
+          }
+        rows += m_tiles * tile_rows;
+      }
+      plan[8 + E] = rows;
+      plan[0] = n;
+      plan[1] = rows;
+      plan[2] = tile_cap;
+      plan[3] = pairs;
+      plan[4] += touched;
+      plan[5] += 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < pairs; i += MP_THREADS) slot[i] += seg[sel[i]];
+    return;
+  }
   const int per = (pairs + MP_THREADS - 1) / MP_THREADS;
   const int p0 = min(tid * per, pairs), p1 = min(p0 + per, pairs);
   for (int e = 0; e < E; ++e) cnt[e * MP_THREADS + tid] = 0;

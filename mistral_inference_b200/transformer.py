@@ -541,6 +541,34 @@ class Transformer(nn.Module):
             out["output.weight"] = self.output_weight
         return out
 
+    # ------------------------------------------------------------------ LoRA, merged path (lora.py:92-155 with args.lora is None)
+    def load_lora(self, lora_path: Union[Path, str], scaling: float = 2.0) -> None:
+        """Loads a LoRA checkpoint and MERGES it into the packed weights (lora.py:93-101,120-139): the forward path is unchanged."""
+        import safetensors.torch
+
+        lora_path = Path(lora_path)
+        assert lora_path.is_file(), f"{lora_path} does not exist or is not a file"
+        self._load_lora_state_dict(safetensors.torch.load_file(str(lora_path)), scaling=scaling)
+
+    def _load_lora_state_dict(self, lora_state_dict: Dict[str, torch.Tensor], scaling: float = 2.0) -> None:
+        """weight <- weight + (lora_B @ lora_A) * scaling for every Linear of this rank except the output layer, with the same
+        torch ops and dtype as the reference (lora.py:129-137).  Un-merged adapters (args.lora set) are outside the hot path."""
+        lora_dtypes = set(p.dtype for p in lora_state_dict.values())
+        assert len(lora_dtypes) == 1, f"LoRA weights have multiple different dtypes {lora_dtypes}. All weights need to have the same dtype"
+        lora_dtype = lora_dtypes.pop()
+        assert lora_dtype == self.dtype, f"LoRA weights dtype differs from model's dtype {lora_dtype} != {self.dtype}"
+        assert all("lora" in key for key in lora_state_dict.keys())
+        assert self.args.lora is None, "un-merged LoRA adapters are outside the accelerated hot path: merge them (args.lora = None)"
+        lora_state_dict = {k: v.to(self.device) for k, v in lora_state_dict.items()}
+        with torch.no_grad():
+            for key, weight in self.state_dict().items():
+                if not key.endswith(".weight") or key == "output.weight" or not key.startswith("layers."):
+                    continue
+                name = key[: -len(".weight")]
+                if (name + ".lora_B.weight") in lora_state_dict:
+                    merged = weight + (lora_state_dict[name + ".lora_B.weight"] @ lora_state_dict[name + ".lora_A.weight"]) * scaling
+                    assert self._assign(key, merged)
+
     @staticmethod
     def empty(args: TransformerArgs, device: Union[torch.device, str] = "cuda", dtype: torch.dtype = torch.bfloat16, **kwargs: Any) -> "Transformer":
         """A model with UNINITIALISED parameters allocated once, directly in `dtype` on `device` (shapes are laid out on `meta`

@@ -122,3 +122,32 @@ def test_cache_metadata_against_oracle_ring():
                 assert kv_len[b] == min(seen[b] + min(s, W), W)
             c.update_seqlens(sl)
             seen = [a + b for a, b in zip(seen, sl)]
+
+
+def test_load_lora_merges_like_the_reference():
+    """Merged LoRA (lora.py:92-139): weight + (B @ A) * scaling lands in the packed buffers under the reference's key names."""
+    import torch
+
+    import mistral_inference_b200 as mi
+    from mistral_inference_b200 import synth
+    from mistral_inference_b200.transformer import Transformer
+
+    p = synth.shape("tiny-moe", n_layers=1)
+    args = mi.TransformerArgs.from_dict(dict(p))
+    m = Transformer(args).to(torch.bfloat16)
+    sd = synth.synth_state_dict(p, 4)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(0)
+    rank = 4
+    lora = {}
+    for name in ("layers.0.attention.wq", "layers.0.attention.wv", "layers.0.attention.wo", "layers.0.feed_forward.experts.3.w1",
+                 "layers.0.feed_forward.experts.3.w2", "layers.0.feed_forward.experts.5.w3"):
+        out_f, in_f = sd[name + ".weight"].shape
+        lora[name + ".lora_A.weight"] = (torch.randn(rank, in_f, generator=g) * 0.1).to(torch.bfloat16)
+        lora[name + ".lora_B.weight"] = (torch.randn(out_f, rank, generator=g) * 0.1).to(torch.bfloat16)
+    m._load_lora_state_dict(lora, scaling=2.0)
+    got = m.state_dict()
+    for key, w in sd.items():
+        name = key[: -len(".weight")]
+        want = w + (lora[name + ".lora_B.weight"] @ lora[name + ".lora_A.weight"]) * 2.0 if (name + ".lora_B.weight") in lora else w
+        assert torch.equal(got[key], want), key

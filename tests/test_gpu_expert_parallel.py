@@ -103,3 +103,68 @@ def test_expert_parallel_equals_unsharded_two_gpus_nccl(top_k):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     _run("nccl", top_k)
+
+
+# ----------------------------------------------------------------------------- reference-compatible pipeline mode on GPUs
+def _pp_worker(rank: int, world: int, port: int, q, backend: str):
+    try:
+        sys.path.insert(0, str(REPO))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dev = rank if backend == "nccl" else 0
+        torch.cuda.set_device(dev)
+        if backend == "nccl":
+            torch.distributed.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+        else:
+            torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+        import mistral_inference_b200 as mi
+        from mistral_inference_b200 import synth
+        from mistral_inference_b200.transformer import Transformer
+
+        p = synth.shape("tiny", n_layers=4, sliding_window=16)
+        sd = synth.synth_state_dict(p, 2, torch.bfloat16, "cuda")
+        args = mi.TransformerArgs.from_dict(dict(p))
+        args.max_batch_size = 2
+        prompts = [synth.synth_prompt(12, p["vocab_size"], 4), synth.synth_prompt(9, p["vocab_size"], 5)]
+        m = Transformer.empty(args, "cuda", torch.bfloat16, pipeline_rank=rank, num_pipeline_ranks=world)
+        m.load_state_dict(sd)
+        toks, lp = mi.generate(prompts, m.eval(), max_tokens=5, temperature=0.0)  # transformer.py:188-237: send / recv / broadcast
+        torch.distributed.barrier()
+        ok, err = True, ""
+        if rank == 0:
+            full = Transformer.empty(args, "cuda", torch.bfloat16)
+            full.load_state_dict(sd)
+            t2, lp2 = mi.generate(prompts, full.eval(), max_tokens=5, temperature=0.0)
+            worst = max(abs(a - b) for x, y in zip(lp, lp2) for a, b in zip(x, y))
+            ok = toks == t2 and worst <= 0.03  # the pipeline's lm head is a bf16 Linear + .float() (transformer.py:235-240), like the single-stage path
+            err = f"tokens {toks} vs {t2}, max|d logprob| {worst}"
+        q.put((rank, ok, 0.0, "" if ok else err))
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    except Exception as e:
+        q.put((rank, False, -1.0, repr(e)))
+        raise
+
+
+def _run_pp(backend: str):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pp_worker, args=(r, 2, port, q, backend)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=400) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+    for rank, ok, _, err in res:
+        assert ok, f"rank {rank}: {err}"
+    assert all(pr.exitcode == 0 for pr in procs)
+
+
+def test_pipeline_ranks_two_processes_one_gpu():
+    _run_pp("gloo")
+
+
+def test_pipeline_ranks_two_gpus_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run_pp("nccl")

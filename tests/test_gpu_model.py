@@ -424,3 +424,20 @@ def test_batched_decode_real_shapes_vs_oracle(shape, over, B, prompt_len, steps)
             d = report(f"{shape} B={B} decode step {step}", got, want)
             check_rows(d, want, cont.rows(probe.end_forward(), [1] * B), f"{shape} B={B} decode step {step}")
             nxt = want.argmax(-1)
+
+
+def test_from_folder_onto_gpu(tmp_path):
+    """Transformer.from_folder (transformer.py:297-338) straight onto the GPU: params.json + consolidated.safetensors streamed into
+    the packed device buffers (allocated once, in the checkpoint dtype); same logits as load_state_dict, bit for bit."""
+    for shape in ("tiny", "tiny-moe"):
+        p = synth.shape(shape, sliding_window=32)
+        folder = synth.write_model_folder(tmp_path / shape, p, seed=1)
+        m1 = Transformer.from_folder(folder, max_batch_size=2, device="cuda")
+        assert m1.dtype == torch.bfloat16 and m1.device.type == "cuda" and m1.args.max_batch_size == 2
+        m2 = gpu_model(p, 2)
+        toks = torch.tensor(synth.synth_prompt(21, p["vocab_size"], 3), device="cuda")
+        c1, c2 = new_cache(m1, 40), new_cache(m2, 40)
+        assert torch.equal(m1.forward(toks, [12, 9], c1), m2.forward(toks, [12, 9], c2))
+        t1, l1 = mi.generate([[1, 2, 3], [4, 5, 6, 7]], m1, max_tokens=5, temperature=0.0)
+        t2, l2 = mi.generate([[1, 2, 3], [4, 5, 6, 7]], m2, max_tokens=5, temperature=0.0)
+        assert t1 == t2 and l1 == l2
