@@ -36,11 +36,8 @@ constexpr int MK_CONSUMERS = MK_CONSUMER_WARPS * 32;
 #define MB200_MK_PRODUCERS 2
 #endif
 constexpr int MK_PRODUCER_WARPS = MB200_MK_PRODUCERS;  // one issuing thread each, stages dealt round-robin (a single thread is ~700 cycles per stage: the stage period)
-#ifndef MB200_MK_PREFETCH
-#define MB200_MK_PREFETCH 0  // experiment: consumers prefetch the first rows of the next phase into registers across grid barriers
-#endif
 #ifndef MB200_MK_WG
-#define MB200_MK_WG MB200_MK_PREFETCH  // the prefetch needs 192 registers per consumer thread: producers in their own warpgroup
+#define MB200_MK_WG 0
 #endif
 #if MB200_MK_WG
 // Experiment (round 2): producers in their own warpgroup so that setmaxnreg can move registers to the consumers (384 threads launch
@@ -338,13 +335,12 @@ struct Producer {
   }
 
   // this CTA's slice of one [N, K] weight matrix, in the stage order consume_matrix expects
-  // skip_first: the consumers fetch (group 0, chunk 0) of this matrix themselves, straight into registers (MB200_MK_PREFETCH)
-  __device__ __forceinline__ void matrix(const bf16* W, int N, int K, bool skip_first = false) {
+  __device__ __forceinline__ void matrix(const bf16* W, int N, int K) {
     const MatCut c = cut_matrix(N, K);
     const uint32_t row_bytes = (uint32_t)c.kc * 2;
     for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
       const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
-      for (int ch = (skip_first && g0 == c.p0) ? 1 : 0; ch < c.nch; ++ch) {
+      for (int ch = 0; ch < c.nch; ++ch) {
         for (int w = 0; w < g; ++w) {
           const bf16* r0 = W + (int64_t)(2 * (g0 + w)) * K;
           uint64_t* bar;
@@ -427,13 +423,12 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
   const int q_dim = p.H * kHeadDim, kv_dim = p.KV * kHeadDim;
   for (int l = 0; l < p.n_layers; ++l) {
     const MkLayer L = p.layers[l];
-    constexpr bool PF = MB200_MK_PREFETCH != 0;
-    pr.matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim, PF);
+    pr.matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim);
     pr.kv_slice(p, L, p.windows[l]);
-    pr.matrix(L.wo, p.dim, q_dim, PF);
+    pr.matrix(L.wo, p.dim, q_dim);
     if (p.n_experts == 0) {
-      pr.matrix(L.w13, 2 * p.hidden, p.dim, PF);
-      pr.matrix(L.w2, p.dim, p.hidden, PF);
+      pr.matrix(L.w13, 2 * p.hidden, p.dim);
+      pr.matrix(L.w2, p.dim, p.hidden);
     } else {
       // expert weights are data dependent: wait for this layer's routing decision (the only point where the weight stream
       // cannot run ahead of the activations)
@@ -444,10 +439,9 @@ __device__ __forceinline__ void producer_main(const MkParams& p, uint8_t* ring, 
       pr.moe_down(p.moe_w2 + l * p.n_experts, sel, p.top_k, p.dim, p.hidden);
     }
   }
-  pr.matrix(p.w_out, p.vocab, p.dim, MB200_MK_PREFETCH != 0);
+  pr.matrix(p.w_out, p.vocab, p.dim);
 }
 
-#if !MB200_MK_PREFETCH
 // ---- consumers: y[pair] = W[pair rows] . xs, epilogue(pair, acc0, acc1) on one lane ----------------
 // Warp-per-pair inside a group: warp w owns pair g0+w and consumes its `nch` stages by itself (32 lanes x 16 B per step,
 // unrolled -> plenty of ILP); only the owning warp releases a slot (empty barriers have arrival count 1).  One block
@@ -508,116 +502,6 @@ __device__ __forceinline__ void consume_matrix(int N, int K, const uint8_t* ring
     consumer_sync();
   }
 }
-
-#else
-// ---- consumers: y[pair] = W[pair rows] . xs, epilogue(pair, acc0, acc1) on one lane ----------------
-// Warp-per-pair inside a group: warp w owns pair g0+w and consumes its `nch` stages by itself (32 lanes x 16 B per step,
-// unrolled -> plenty of ILP); only the owning warp releases a slot (empty barriers have arrival count 1).  One block
-// barrier per GROUP keeps all warps within a group of each other (see the stage-order note above).
-// `pre(n)` runs on the finishing lane BEFORE the pair's stages are consumed and its result is handed to `epi`: loads the
-// epilogue needs (the residual) are then off the critical path of the phase's last pair (an L2 round trip right before the
-// barrier's release store: measured 3.2-4.2 us barrier latency after wo / down vs 1.75 us after gate/up, which loads nothing).
-//
-// Register prefetch across grid barriers (`preload`; build with -DMB200_MK_PREFETCH=1).  The 12-stage shared-memory ring buffers ~4.4 us of this SM's HBM share; a phase
-// boundary (grid barrier + staging of the next activation vector + arrival skew) that lasts longer stalls the weight stream.
-// Weights do not depend on activations, so the caller ARRIVES at the grid barrier, then calls consume_matrix, which first pulls
-// each warp's first stage of this phase (group 0, chunk 0) out of the ring into registers (16 KB = 128 registers per lane) and
-// releases the slot, and only then runs `between()` -- the barrier wait plus the staging of this phase's input vector.  That is
-// 8 more stages (+2.9 us) of buffering exactly where the bubbles are; the stage sequence itself is unchanged.
-constexpr int MK_PL = MK_MAX_KC / 8 / 32;  // uint4 per row per lane in a full stage (16)
-template <class Between, class Pre, class Epi>
-__device__ __forceinline__ void consume_matrix(const bf16* W, int N, int K, const uint8_t* ring, uint64_t* full, uint64_t* empty, int n_stages, RingState& rs,
-                                               const uint4* xs, int tid, bool preload, Between between, Pre pre, Epi epi) {
-  const MatCut c = cut_matrix(N, K);
-  const int lane = tid & 31, warp = tid >> 5;
-  const int kc8 = c.kc >> 3;  // 16-byte chunks per row chunk
-  uint4 pa[MK_PL], pb[MK_PL];
-  const int g_first = min(MK_CONSUMER_WARPS, c.p1 - c.p0);
-  const bool have = preload && warp < g_first;  // warp-uniform
-  {
-    // rows 2 (p0 + warp), 2 (p0 + warp) + 1 of W, K-chunk 0: straight from global memory, no mbarrier, nothing to wait for here
-    const uint4* w0 = reinterpret_cast<const uint4*>(W + (int64_t)(2 * (c.p0 + (have ? warp : 0))) * K);
-    const uint4* w1 = w0 + (K >> 3);
-#pragma unroll
-    for (int u = 0; u < MK_PL; ++u) {
-      const int i = lane + 32 * u;
-      pa[u] = pb[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (have && i < kc8) {
-        pa[u] = ldg_stream16(w0 + i);
-        pb[u] = ldg_stream16(w1 + i);
-      }
-    }
-  }
-  between();
-  for (int g0 = c.p0; g0 < c.p1; g0 += MK_CONSUMER_WARPS) {
-    const int g = min(MK_CONSUMER_WARPS, c.p1 - g0);
-    float a0 = 0.f, a1 = 0.f;
-    uint2 prefetched = make_uint2(0u, 0u);
-    if (warp < g && lane == 0) prefetched = pre(2 * (g0 + warp));
-    for (int ch = 0; ch < c.nch; ++ch) {
-      if (have && ch == 0 && g0 == c.p0) {
-        // this stage sits in registers; its slot is already released
-#pragma unroll
-        for (int u = 0; u < MK_PL; ++u) {
-          const int i = lane + 32 * u;
-          if (i < kc8) {
-            uint4 a = pa[u], b = pb[u];
-            // scheduling fence: without it the compiler hoists the bf16 -> fp32 unpacking of all 128 weight registers (256 live
-            // values) to the top of the block and spills; tying this step's inputs to the running sums keeps the steps in order
-            asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w), "+f"(a0), "+f"(a1));
-            const uint4 x = xs[i];
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
-              a0 = fmaf(bf16lo(aw[j]), xl, a0);
-              a0 = fmaf(bf16hi(aw[j]), xh, a0);
-              a1 = fmaf(bf16lo(bw[j]), xl, a1);
-              a1 = fmaf(bf16hi(bw[j]), xh, a1);
-            }
-          }
-        }
-      } else if (warp < g) {
-        const int ch_ring = (preload && g0 == c.p0) ? ch - 1 : ch;  // the producer skips (group 0, chunk 0) of a prefetched phase
-        const uint32_t it = rs.it + (uint32_t)(ch_ring * g + warp);
-        const uint32_t slot = it % n_stages, par = (it / n_stages) & 1;
-        // Guard (tests/test_megakernel_protocol.py): bulk copies land out of order, so this warp may get here before the
-        // slot's PREVIOUS fill (owned by another warp) has landed; `full` would then still be one phase behind and a
-        // parity wait would alias and pass early.  Waiting first until that previous fill has been CONSUMED (same
-        // condition the producer waits for before refilling) pins `full` to phase {r, r+1} when it is tested.
-        mbar_wait(&empty[slot], par ^ 1, 2, it);
-        mbar_wait(&full[slot], par, 3, it);
-        const uint4* w0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * MK_STAGE_BYTES);
-        const uint4* w1 = w0 + kc8;
-        const uint4* xc = xs + ch * kc8;
-#pragma unroll 4
-        for (int i = lane; i < kc8; i += 32) {
-          const uint4 a = w0[i], b = w1[i], x = xc[i];
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
-            a0 = fmaf(bf16lo(aw[j]), xl, a0);
-            a0 = fmaf(bf16hi(aw[j]), xh, a0);
-            a1 = fmaf(bf16lo(bw[j]), xl, a1);
-            a1 = fmaf(bf16hi(bw[j]), xh, a1);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_n(&empty[slot], MK_CONSUMER_WARPS);  // this warp is the only reader of the slot
-      }
-    }
-    if (warp < g) {
-      a0 = warp_sum(a0);
-      a1 = warp_sum(a1);
-      if (lane == 0) epi(2 * (g0 + warp), a0, a1, prefetched);
-    }
-    rs.it += (uint32_t)(g * ((preload && g0 == c.p0) ? c.nch - 1 : c.nch));
-    consumer_sync();
-  }
-}
-
-#endif
 
 // ---- consumers: stage an activation vector (written by other CTAs: L2 loads) and optionally RMS-normalise it ----
 __device__ __forceinline__ void stage_x(uint4* xs, const bf16* src, const bf16* norm_w, int K, float eps, float* red, int tid) {
@@ -993,7 +877,6 @@ __device__ __forceinline__ void consume_moe_down(const MkParams& p, const MoeRou
   }
 }
 
-#if !MB200_MK_PREFETCH
 template <int REP>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1202,246 +1085,5 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParam
   }
   (void)epoch0;
 }
-
-#else
-template <int REP>
-__global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [ring: n_stages x 16 KB][xs: xs_bytes][barriers][reduction scratch]
-  uint8_t* ring = smem;
-  uint4* xs = reinterpret_cast<uint4*>(smem + (size_t)p.n_stages * MK_STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + p.xs_bytes);
-  uint64_t* empty = full + MK_MAX_STAGES;
-  float* red = reinterpret_cast<float*>(empty + MK_MAX_STAGES);                       // [8]
-  MoeRoute* route = reinterpret_cast<MoeRoute*>(red + 48);                            // routing decision of the current MoE layer
-  uint64_t* route_bar = reinterpret_cast<uint64_t*>(route + 1);                       // consumers -> producers: "route is valid"
-
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int i = 0; i < p.n_stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], MK_CONSUMER_WARPS);  // weight stages: the owning warp arrives x8; K/V stages: every warp x1
-    }
-    mbar_init(route_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int q_dim = p.H * kHeadDim, kv_dim = p.KV * kHeadDim;
-  RingState rs;
-  rs.it = 0;
-
-  if (tid >= MK_CONSUMERS) {
-    // ================= producers (one thread per producer warp; weights and old K/V rows never wait for activations) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-    const int pw = (tid - MK_CONSUMERS) >> 5;
-    if ((tid & 31) == 0 && pw < MK_PRODUCER_WARPS) producer_main(p, ring, full, empty, pw, route, route_bar);
-    return;
-  }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-
-  // ================= consumer warps =================
-  // barriers completed by previous launches on this workspace.  Nobody writes the word until every CTA of this launch has
-  // finished (see the end of the kernel), and launches are stream ordered, so this read cannot race.
-  unsigned epoch = ld_acquire_u32(p.bar_epoch);
-  const int64_t token = *p.token;
-  const bool preload = true;  // compile-time variant: the producer's schedule skips the prefetched stages
-  // Every weight phase is entered as  grid_arrive(previous phase) ; consume_matrix(..., between = { grid_wait ; stage input })
-  // so that the register preload (see consume_matrix) overlaps the barrier.
-  for (int l = 0; l < p.n_layers; ++l) {
-    const MkLayer L = p.layers[l];
-    const int W = p.windows[l];
-    const bf16* x_in = (l == 0) ? p.emb + token * p.dim : p.xbuf + (size_t)(l & 1) * p.dim;
-    bf16* x_out = p.xbuf + (size_t)((l + 1) & 1) * p.dim;
-
-    // ---- phase 1: RMSNorm + QKV + RoPE + ring scatter ----
-    mk_stamp(p, tid, l, 0);
-    {
-      const int slot_row = p.batch_row * W + p.pos % W;
-      const float* rope_row = p.rope + (int64_t)p.pos * (kHeadDim / 2) * 2;
-      bf16* ck = L.cache_k + (int64_t)slot_row * kv_dim;
-      bf16* cv = L.cache_v + (int64_t)slot_row * kv_dim;
-      consume_matrix(L.wqkv, q_dim + 2 * kv_dim, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       if (l > 0) {  // the barrier that ends the previous layer
-                         grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                         bar_stamp(p, tid, l - 1, 5, 1);
-                         mk_stamp(p, tid, l - 1, 11);
-                       }
-                       stage_x(xs, x_in, L.attn_norm, p.dim, p.eps, red, tid);
-                       mk_stamp(p, tid, l, 1);
-                     },
-                     [&](int n) { return *reinterpret_cast<const uint2*>(rope_row + ((n & (kHeadDim - 1)) >> 1) * 2); },
-                     [&](int n, float a0, float a1, uint2 pf) {
-        const float y0 = round_bf16(a0), y1 = round_bf16(a1);
-        if (n < q_dim + kv_dim) {
-          const float2 cs = make_float2(__uint_as_float(pf.x), __uint_as_float(pf.y));
-          float re, im;
-          ref_cmul(y0, y1, cs.x, cs.y, re, im);
-          const uint32_t packed = pack_bf16x2(re, im);
-          if (n < q_dim)
-            *reinterpret_cast<uint32_t*>(p.qbuf + n) = packed;
-          else
-            *reinterpret_cast<uint32_t*>(ck + (n - q_dim)) = packed;
-        } else {
-          *reinterpret_cast<uint32_t*>(cv + (n - q_dim - kv_dim)) = pack_bf16x2(y0, y1);
-        }
-      });
-    }
-    mk_stamp(p, tid, l, 2);
-    grid_barrier(p, tid, epoch, l, 0);
-    mk_stamp(p, tid, l, 3);
-
-    // ---- phase 2a: partial attention of my position slice;  2b: merge the slices ----
-    if (attn_slice(p, W).pps == 16)
-      mk_attention_slice<REP, 16>(p, L, W, ring, full, empty, p.n_stages, rs, tid, l);
-    else
-      mk_attention_slice<REP, 8>(p, L, W, ring, full, empty, p.n_stages, rs, tid, l);
-    mk_stamp(p, tid, l, 12);
-    grid_barrier(p, tid, epoch, l, 1);
-    mk_stamp(p, tid, l, 13);
-    mk_attention_combine(p, W, tid, reinterpret_cast<float*>(xs));
-    mk_stamp(p, tid, l, 4);
-    grid_arrive(p, tid, epoch, l, 2);
-
-    // ---- phase 3: wo + residual ----
-    consume_matrix(L.wo, p.dim, q_dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                   [&]() {
-                     grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                     bar_stamp(p, tid, l, 2, 1);
-                     mk_stamp(p, tid, l, 5);
-                     stage_x(xs, p.abuf, nullptr, q_dim, 0.f, red, tid);
-                   },
-                   [&](int n) { return make_uint2(ldcg_u32(x_in + n), 0u); },
-                   [&](int n, float a0, float a1, uint2 pf) {
-                     const uint32_t r = pf.x;
-                     *reinterpret_cast<uint32_t*>(p.hbuf + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
-                   });
-    mk_stamp(p, tid, l, 6);
-    grid_arrive(p, tid, epoch, l, 3);
-
-    if (p.n_experts == 0) {
-      // ---- phase 4: RMSNorm + gate/up + SiLU*mul ----
-      consume_matrix(L.w13, 2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                       bar_stamp(p, tid, l, 3, 1);
-                       mk_stamp(p, tid, l, 7);
-                       stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-                     },
-                     [&](int) { return make_uint2(0u, 0u); },
-                     [&](int n, float a0, float a1, uint2) {
-                       const float s = round_bf16(ref_silu(round_bf16(a0)));
-                       p.gbuf[n >> 1] = __float2bfloat16_rn(s * round_bf16(a1));
-                     });
-      mk_stamp(p, tid, l, 8);
-      grid_arrive(p, tid, epoch, l, 4);
-
-      // ---- phase 5: down + residual ----
-      // (Tried: no full barrier here -- stage g chunk by chunk as the barrier words of the CTA range that produced each K-chunk
-      //  complete.  Correct, but 4 polling rounds + 4 block syncs cost more than the ~5 us gate/up arrival skew they hide.)
-      consume_matrix(L.w2, p.dim, p.hidden, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                     [&]() {
-                       grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                       bar_stamp(p, tid, l, 4, 1);
-                       mk_stamp(p, tid, l, 9);
-                       stage_x(xs, p.gbuf, nullptr, p.hidden, 0.f, red, tid);
-                     },
-                     [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
-                     [&](int n, float a0, float a1, uint2 pf) {
-                       const uint32_t r = pf.x;
-                       *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(round_bf16(a0) + bf16lo(r), round_bf16(a1) + bf16hi(r));
-                     });
-    } else {
-      // ---- phase 4 (MoE): RMSNorm + router; gate/up + SiLU*mul of the selected experts (ascending expert index) ----
-      // (no register preload: the expert weight stream itself waits for the routing decision)
-      grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-      bar_stamp(p, tid, l, 3, 1);
-      mk_stamp(p, tid, l, 7);
-      stage_x(xs, p.hbuf, L.ffn_norm, p.dim, p.eps, red, tid);
-      moe_route(p, l, xs, red, route, route_bar, tid);
-      const MoeRoute rt = *route;
-      for (int j = 0; j < p.top_k; ++j) {
-        bf16* gj = p.gbuf + (size_t)j * p.hidden;
-        consume_matrix(p.moe_w13[l * p.n_experts + rt.e[j]], 2 * p.hidden, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, false, [&]() {}, [&](int) { return make_uint2(0u, 0u); },
-                       [&](int n, float a0, float a1, uint2) {
-                         const float sv = round_bf16(ref_silu(round_bf16(a0)));
-                         gj[n >> 1] = __float2bfloat16_rn(sv * round_bf16(a1));
-                       });
-      }
-      mk_stamp(p, tid, l, 8);
-      grid_barrier(p, tid, epoch, l, 4);
-      mk_stamp(p, tid, l, 9);
-      // ---- phase 5 (MoE): expert down projections, weighted bf16 accumulation in expert order, + residual ----
-      stage_x(xs, p.gbuf, nullptr, p.top_k * p.hidden, 0.f, red, tid);
-      consume_moe_down(p, rt, ring, full, empty, p.n_stages, rs, xs, tid, [&](int n) { return make_uint2(ldcg_u32(p.hbuf + n), 0u); },
-                       [&](int n, float r0, float r1, uint2 pf) {
-                         *reinterpret_cast<uint32_t*>(x_out + n) = pack_bf16x2(r0 + bf16lo(pf.x), r1 + bf16hi(pf.x));
-                       });
-    }
-    mk_stamp(p, tid, l, 10);
-    grid_arrive(p, tid, epoch, l, 5);  // waited for at the top of the next layer (or before the lm head)
-  }
-
-  // ---- final RMSNorm + lm head (fp32 logits, each a bf16-rounded value) + greedy argmax ----
-  // argmax key: order-preserving map of the fp32 logit in the high word, ~index in the low word, so that the maximum key is
-  // the largest logit and, among equal logits, the SMALLEST index (what torch.argmax returns; generate.py:156)
-  unsigned long long best = 0ull;
-  auto key_of = [](float v, int idx) {
-    unsigned u = __float_as_uint(v);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    return ((unsigned long long)u << 32) | (unsigned)(0x7fffffff - idx);
-  };
-  consume_matrix(p.w_out, p.vocab, p.dim, ring, full, empty, p.n_stages, rs, xs, tid, preload,
-                 [&]() {
-                   if (p.n_layers > 0) {
-                     grid_wait(p, tid, epoch, 0, MK_BAR_WORDS - 1);
-                     bar_stamp(p, tid, p.n_layers - 1, 5, 1);
-                     mk_stamp(p, tid, p.n_layers - 1, 11);
-                   }
-                   stage_x(xs, p.xbuf + (size_t)(p.n_layers & 1) * p.dim, p.final_norm, p.dim, p.eps, red, tid);
-                 },
-                 [&](int) { return make_uint2(0u, 0u); },
-                 [&](int n, float a0, float a1, uint2) {
-                   const float y0 = round_bf16(a0), y1 = round_bf16(a1);
-                   *reinterpret_cast<float2*>(p.logits + n) = make_float2(y0, y1);
-                   const unsigned long long k0 = key_of(y0, n), k1 = key_of(y1, n + 1);
-                   best = max(best, max(k0, k1));
-                 });
-  if (p.next_token != nullptr) {
-    // lane 0 of every warp holds its pairs' best; CTA reduce through shared memory, then the last CTA to arrive reduces all
-    unsigned long long* sm_best = reinterpret_cast<unsigned long long*>(xs);
-    consumer_sync();
-    if ((tid & 31) == 0) sm_best[tid >> 5] = best;
-    consumer_sync();
-    if (tid == 0) {
-      unsigned long long b = 0ull;
-#pragma unroll
-      for (int w = 0; w < MK_CONSUMER_WARPS; ++w) b = max(b, sm_best[w]);
-      p.argmax_slots[blockIdx.x] = b;
-      __threadfence();
-      const int prev = atomicAdd(p.argmax_counter, 1);
-      if (prev == (int)gridDim.x - 1) {
-        *p.argmax_counter = 0;
-        __threadfence();
-        unsigned long long g = 0ull;
-        for (int c = 0; c < (int)gridDim.x; ++c) g = max(g, __ldcg(p.argmax_slots + c));
-        *p.next_token = (long long)(0x7fffffff - (int)(g & 0xffffffffull));
-      }
-    }
-  }
-  // publish the barrier epoch for the next launch: the last CTA to get here (all CTAs are past every barrier by then)
-  consumer_sync();
-  if (tid == 0) {
-    __threadfence();
-    const int prev = atomicAdd(p.done_counter, 1);
-    if (prev == (int)gridDim.x - 1) {
-      *p.done_counter = 0;
-      st_release_u32(p.bar_epoch, epoch);
-    }
-  }
-}
-
-#endif
 
 }  // namespace mb200

@@ -91,16 +91,21 @@ class Contamination:
         self.moe = moe
 
     def rows(self, margins: torch.Tensor, seqlens) -> torch.Tensor:
-        """`margins` [T] of this forward -> exempt mask [T] (a prefill row is exempt if ANY earlier-or-same token of its sequence
-        in this chunk is risky: causal attention only looks back; conservatively the whole sequence's chunk is flagged)."""
+        """`margins` [T] of this forward -> exempt mask [T]: a row is exempt iff a token AT OR BEFORE it in its sequence (this chunk
+        or an earlier forward) sits on a router near-tie -- causal attention only looks back, so earlier rows of the chunk are held."""
         if not self.moe:
             return None
-        seq = row_seq(seqlens)
         risky = margins <= RISKY_ULPS
-        for b in range(len(seqlens)):
-            if risky[seq == b].any():
+        out = torch.zeros(int(sum(seqlens)), dtype=torch.bool)
+        o = 0
+        for b, n in enumerate(seqlens):
+            r = risky[o:o + n]
+            seen = self.flag[b] | (torch.cumsum(r.to(torch.int32), 0) > 0)
+            out[o:o + n] = seen
+            if r.any():
                 self.flag[b] = True
-        return self.flag[seq]
+            o += n
+        return out
 
 
 @pytest.mark.parametrize("name", BF16_CASES)
