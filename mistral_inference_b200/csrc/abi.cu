@@ -308,7 +308,7 @@ int mb200_moe_sizes(int64_t T, int64_t n_experts, int64_t top_k, int64_t* tile_r
   const int64_t cap = moe_tile_cap(T * top_k, n_experts, tr);
   if (tile_rows) *tile_rows = tr;
   if (rows_cap) *rows_cap = cap * tr;
-  if (plan_words) *plan_words = MOE_PLAN_HEADER + 2 * cap;
+  if (plan_words) *plan_words = moe_plan_words(T * top_k, n_experts, tr);
   return MB200_OK;
 }
 

@@ -147,7 +147,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // GROUPED = true (mixture of experts, csrc/moe.cuh): the A rows are the (token, expert) pairs sorted by expert, every expert's
 // segment padded to a multiple of TA rows; m tile i covers rows plan.tile_row0[i] .. + TA of expert plan.tile_expert[i], whose
 // weight matrix has its own tensor map (map_w[expert]).  The number of m tiles is DEVICE data (no host sync after routing).
-constexpr int MOE_PLAN_HEADER = 64;  // int32 words: [0] m tiles of this rank, [1] padded rows in total, [2] tile capacity, [8..] segment starts
+constexpr int MOE_PLAN_HEADER = 64;  // int32 words: [0] m tiles of this rank, [1] padded rows in total, [2] tile capacity, [6] tile pairs, [8..] segment starts
+// after the header: tile_expert[cap], tile_row0[cap], pair_expert[cap], pair_info[cap] (cap = plan[2]).  A PAIR is two vertically
+// adjacent m tiles of ONE expert (or a single last tile: bit 30 of pair_info clear), the unit of the 2-CTA cluster variant.
+constexpr int MOE_PAIR_SECOND = 1 << 30;
 constexpr int MOE_MAX_EXPERTS = 16;  // tensor maps travel as kernel parameters (128 B each)
 struct MoeWeightMaps {
   CUtensorMap m[MOE_MAX_EXPERTS];
@@ -156,7 +159,6 @@ struct MoeWeightMaps {
 template <int MODE, int CL, int BN, int TA, bool GROUPED>
 __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUtensorMap* map_w_base, const TcGemmParams& p, const int32_t* plan) {
   static_assert(TA == 128 || CL == 1, "small-batch variant is single-CTA");
-  static_assert(!GROUPED || CL == 1, "grouped variant is single-CTA");
   using Cfg = TgCfg<BN, TA>;
   constexpr int TG_STAGES = Cfg::kStages, TG_B_BYTES = Cfg::kBBytes, TG_STAGE_BYTES = Cfg::kStageBytes, TG_TMEM_COLS = Cfg::kTmemCols;
   constexpr int TG_A_BYTES = Cfg::kABytes;  // shadows the 128-row constant
@@ -174,10 +176,22 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int cta = (int)blockIdx.x / CL, n_cta = (int)gridDim.x / CL;  // cluster index / clusters in the grid
   // a cluster walks "super tiles" of CL vertically adjacent tiles; rows past T read as zeros (TMA) and are never stored
-  const int num_m = GROUPED ? plan[0] : ((p.T + TG_BM - 1) / TG_BM + CL - 1) / CL;
+  // grouped: m units are the plan's tiles (single CTA) or tile pairs (cluster of two)
+  const int num_m = GROUPED ? (CL > 1 ? plan[6] : plan[0]) : ((p.T + TG_BM - 1) / TG_BM + CL - 1) / CL;
   const int num_n = p.N / TG_BN, num_tiles = num_m * num_n, num_k = p.K / TG_BK;
-  const int32_t* tile_expert = GROUPED ? plan + MOE_PLAN_HEADER : nullptr;
-  const int32_t* tile_row0 = GROUPED ? plan + MOE_PLAN_HEADER + plan[2] : nullptr;
+  const int32_t* tile_expert = GROUPED ? plan + MOE_PLAN_HEADER + (CL > 1 ? 2 * plan[2] : 0) : nullptr;
+  const int32_t* tile_row0 = GROUPED ? tile_expert + plan[2] : nullptr;
+  // first row of this CTA's m tile of unit `u` (cluster rank 1 takes the pair's second tile; a missing second tile is recomputed
+  // from the first one's rows and not stored)
+  auto grouped_m0 = [&](int u, bool& store) {
+    const int info = tile_row0[u];
+    store = true;
+    if (CL == 1) return info;
+    const int row0 = info & (MOE_PAIR_SECOND - 1);
+    if (rank == 0) return row0;
+    store = (info & MOE_PAIR_SECOND) != 0;
+    return store ? row0 + TG_BM : row0;
+  };
   const CUtensorMap& map_w = *map_w_base;
 
   if (threadIdx.x == 0) {
@@ -207,7 +221,8 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = cta; tile < num_tiles; tile += n_cta) {
-        const int m0 = GROUPED ? tile_row0[tile % num_m] : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
+        bool store_unused;
+        const int m0 = GROUPED ? grouped_m0(tile % num_m, store_unused) : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
         const CUtensorMap* wmap = GROUPED ? map_w_base + tile_expert[tile % num_m] : map_w_base;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const uint32_t s = it % TG_STAGES, par = (it / TG_STAGES) & 1;
@@ -216,7 +231,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           uint8_t* sa = smem + s * TG_STAGE_BYTES;
           tma_load_2d(sa, &map_a, &full[s], kb * TG_BK, m0);
           if (CL > 1)
-            tma_load_2d_multicast(sa + TG_A_BYTES + rank * (TG_B_BYTES / CL), &map_w, &full[s], kb * TG_BK, n0 + rank * (TG_BN / CL),
+            tma_load_2d_multicast(sa + TG_A_BYTES + rank * (TG_B_BYTES / CL), wmap, &full[s], kb * TG_BK, n0 + rank * (TG_BN / CL),
                                   (uint16_t)((1u << CL) - 1));
           else
             tma_load_2d(sa + TG_A_BYTES, wmap, &full[s], kb * TG_BK, n0);
@@ -254,12 +269,13 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
     const int lane_base = (warp & 3) * 32;
     uint32_t acc_it = 0;
     for (int tile = cta; tile < num_tiles; tile += n_cta, ++acc_it) {
-      const int m0 = GROUPED ? tile_row0[tile % num_m] : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
+      bool store = true;
+      const int m0 = GROUPED ? grouped_m0(tile % num_m, store) : ((tile % num_m) * CL + rank) * TG_BM, n0 = (tile / num_m) * TG_BN;
       const uint32_t acc = acc_it & 1, acc_par = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_par, 14, acc_it);
       tc_fence_after();
       // accumulator rows >= TA were computed from whatever follows the short A box in shared memory: never stored
-      const int t = (TA == 128 || lane_base + lane < TA) ? m0 + lane_base + lane : 0x7fffffff;
+      const int t = (store && (TA == 128 || lane_base + lane < TA)) ? m0 + lane_base + lane : 0x7fffffff;
       // two register buffers: the TMEM load of chunk c+1 is in flight while chunk c goes through the epilogue
       const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * TG_BN;
       uint32_t va[32], vb[32];
@@ -297,11 +313,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1)
   tc_gemm_body<MODE, CL, BN, TA, false>(map_a, &map_w, p, nullptr);
 }
 
-template <int MODE, int BN, int TA>
+template <int MODE, int CL, int BN, int TA>
 __global__ void __launch_bounds__(TG_THREADS, 1)
     gemm_tcgen05_grouped_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ MoeWeightMaps maps_w, const TcGemmParams p,
                                 const int32_t* __restrict__ plan) {
-  tc_gemm_body<MODE, 1, BN, TA, true>(map_a, maps_w.m, p, plan);
+  tc_gemm_body<MODE, CL, BN, TA, true>(map_a, maps_w.m, p, plan);
 }
 
 // ---- host: tensor maps (driver API through the runtime's entry-point lookup, no libcuda link dependency) ----

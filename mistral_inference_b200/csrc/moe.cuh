@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(MP_THREADS) moe_plan_kernel(const int32_t* __r
       plan[3] = pairs;
       plan[4] += touched;
       plan[5] += 1;
+      plan[6] = 0;  // decode-sized calls never take the cluster variant
     }
     __syncthreads();
     for (int i = tid; i < pairs; i += MP_THREADS) slot[i] += seg[sel[i]];
@@ -185,18 +186,24 @@ __global__ void __launch_bounds__(MP_THREADS) moe_plan_kernel(const int32_t* __r
   }
   __syncthreads();
   if (tid == 0) {
-    int rows = 0, n = 0;
+    int rows = 0, n = 0, np = 0;
     for (int e = 0; e < E; ++e) {
       seg[e] = rows;
       plan[8 + e] = rows;
       const int m_tiles = (total[e] + tile_rows - 1) / tile_rows;
-      if (e % shard_world == shard_rank)
+      if (e % shard_world == shard_rank) {
         for (int m = 0; m < m_tiles && n < tile_cap; ++m, ++n) {
           plan[MOE_PLAN_HEADER + n] = e;
           plan[MOE_PLAN_HEADER + tile_cap + n] = rows + m * tile_rows;
         }
+        for (int m = 0; m < m_tiles && np < tile_cap; m += 2, ++np) {  // pairs of vertically adjacent tiles for the 2-CTA cluster GEMM
+          plan[MOE_PLAN_HEADER + 2 * tile_cap + np] = e;
+          plan[MOE_PLAN_HEADER + 3 * tile_cap + np] = (rows + m * tile_rows) | (m + 1 < m_tiles ? MOE_PAIR_SECOND : 0);
+        }
+      }
       rows += m_tiles * tile_rows;
     }
+    plan[6] = np;
     seg[E] = rows;
     plan[8 + E] = rows;
     plan[0] = n;
@@ -337,9 +344,10 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(const MoeCombineParams
 // ---- host side -------------------------------------------------------------------------------------------------------------
 inline int moe_tile_rows(int64_t T) { return T <= 32 ? 32 : (T <= 64 ? 64 : 128); }  // an expert gets at most one row per token: decode batches fit ONE short m tile
 inline int64_t moe_tile_cap(int64_t pairs, int64_t E, int tile_rows) { return (pairs + tile_rows - 1) / tile_rows + E; }
+inline int64_t moe_plan_words(int64_t pairs, int64_t E, int tile_rows) { return MOE_PLAN_HEADER + 4 * moe_tile_cap(pairs, E, tile_rows); }
 inline int64_t moe_row_cap(int64_t pairs, int64_t E, int tile_rows) { return moe_tile_cap(pairs, E, tile_rows) * tile_rows; }
 
-template <int MODE, int BN, int TA>
+template <int MODE, int BN, int TA, int CL = 1>
 int launch_grouped_bn(const void* a, int64_t rows_cap, int64_t K, int64_t N, const void* const* w_host, int E, const int32_t* plan, const EpiParams& epi,
                       int sms, cudaStream_t stream) {
   using Cfg = TgCfg<BN, TA>;
@@ -353,7 +361,7 @@ int launch_grouped_bn(const void* a, int64_t rows_cap, int64_t K, int64_t N, con
       maps.m[e] = map_a;
       continue;
     }
-    rc = make_tensor_map_2d(&maps.m[e], w, N, K, BN);
+    rc = make_tensor_map_2d(&maps.m[e], w, N, K, BN / CL);  // cluster pairs: each CTA fetches half of the W tile and multicasts it
     if (rc) return rc;
   }
   TcGemmParams p;
@@ -361,9 +369,26 @@ int launch_grouped_bn(const void* a, int64_t rows_cap, int64_t K, int64_t N, con
   p.N = (int)N;
   p.K = (int)K;
   p.epi = epi;
-  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_grouped_kernel<MODE, BN, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-  gemm_tcgen05_grouped_kernel<MODE, BN, TA><<<sms, TG_THREADS, Cfg::kSmem, stream>>>(map_a, maps, p, plan);
-  MB_CHECK_LAUNCH("gemm_tcgen05_grouped_kernel");
+  MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_grouped_kernel<MODE, CL, BN, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  if (CL == 1) {
+    gemm_tcgen05_grouped_kernel<MODE, CL, BN, TA><<<sms, TG_THREADS, Cfg::kSmem, stream>>>(map_a, maps, p, plan);
+    MB_CHECK_LAUNCH("gemm_tcgen05_grouped_kernel");
+    return MB200_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2u * (unsigned)(sms / 2));
+  cfg.blockDim = dim3(TG_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_grouped_kernel<MODE, CL, BN, TA>, map_a, maps, p, plan));
+  MB_CHECK_LAUNCH("gemm_tcgen05_grouped_kernel<cluster 2>");
   return MB200_OK;
 }
 
@@ -413,6 +438,9 @@ int launch_grouped(const void* a, int64_t rows_cap, int64_t K, int64_t N, const 
     return launch_grouped_streamk<MODE, 64>(a, rows_cap, K, N, w_host, E, plan, epi, workspace, workspace_bytes, header, sms, stream);
   }
   if (tile_rows == 128) {
+    // enough rows per expert for vertically adjacent tile pairs: the 2-CTA cluster kernel (W tile multicast, 2/3 of the L2 -> SM traffic)
+    if (N % 256 == 0 && tcgen05_cluster_enabled() && rows_cap >= (int64_t)E * 512)
+      return launch_grouped_bn<MODE, 256, 128, 2>(a, rows_cap, K, N, w_host, E, plan, epi, sms, stream);
     if (N % 256 == 0) return launch_grouped_bn<MODE, 256, 128>(a, rows_cap, K, N, w_host, E, plan, epi, sms, stream);
     if (N % 128 == 0) return launch_grouped_bn<MODE, 128, 128>(a, rows_cap, K, N, w_host, E, plan, epi, sms, stream);
     if (N % 64 == 0) return launch_grouped_bn<MODE, 64, 128>(a, rows_cap, K, N, w_host, E, plan, epi, sms, stream);

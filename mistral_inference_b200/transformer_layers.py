@@ -104,8 +104,10 @@ class Attention(nn.Module):
 
 
 def decode_splits(B: int, KV: int, W: int, n_sm: int = 148) -> int:
-    """KV splits per (sequence, kv head): about two CTAs per SM, at least 64 keys per split."""
-    s = max(1, (2 * n_sm + B * KV - 1) // (B * KV))
+    """KV splits per (sequence, kv head): as many as fit ONE wave of two CTAs per SM (a second, partial wave costs more than the
+    idle SMs of an incomplete first one; with B * KV >= 2 * n_sm / 2 there is no split and no combine step at all), at least 64
+    keys per split."""
+    s = max(1, (2 * n_sm) // (B * KV))
     return int(max(1, min(s, 64, (W + 63) // 64)))
 
 

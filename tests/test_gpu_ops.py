@@ -519,7 +519,8 @@ def _router_margin_ulps(x, gate_w, k):
     return (top[:, k - 1] - top[:, k]) / ulp
 
 
-@pytest.mark.parametrize("T,dim,hid,k", [(5, 256, 256, 2), (37, 256, 256, 3), (200, 256, 512, 2), (16, 4096, 14336, 2), (300, 4096, 14336, 2)])
+@pytest.mark.parametrize("T,dim,hid,k", [(5, 256, 256, 2), (37, 256, 256, 3), (200, 256, 512, 2), (16, 4096, 14336, 2), (300, 4096, 14336, 2),
+                                         (2500, 256, 512, 2)])  # last: enough rows per expert for the 2-CTA cluster pairs of the grouped GEMM
 def test_moe_route_grouped_ffn_vs_oracle(T, dim, hid, k):
     """mb200_moe_route + mb200_moe_grouped_ffn against the oracle's MoE (moe.py:24-32) + residual: routing decisions and weights
     exactly (tokens whose k-th / (k+1)-th router logits are within 2 ulps excepted), the deterministic row plan exactly, the
