@@ -33,7 +33,7 @@ import torch
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
-from mistral_inference_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 
 METRIC = "decode tokens/sec (bf16, batch=1, seq=4k) [+ prefill TFLOPS, both vs roofline]"
 

@@ -5,7 +5,7 @@ Run in the build container (where /root/reference exists):   python -m oracle.ma
 The reference cannot travel to the GPU box, so its outputs on small seeded cases are committed as
 fixtures.  Each fixture holds the outputs of the reference's own `Transformer.forward` /
 `generate` (mistral_inference/transformer.py:221-242, generate.py:43-148) imported behind
-oracle/ref_shims.py, on weights from mistral_inference_b200.synth (bit-reproducible anywhere).
+oracle/ref_shims.py, on weights from synth (bit-reproducible anywhere).
 
 Cases follow SURVEY.md section 8c "tests to carry over": ragged batch greedy decode; ring that
 wraps (sliding_window < length); list-valued sliding_window; 8-expert top-2 MoE;
@@ -22,7 +22,7 @@ REPO = Path(__file__).resolve().parents[1]
 if str(REPO) not in sys.path:
     sys.path.insert(0, str(REPO))
 
-from mistral_inference_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 from oracle import ref_shims  # noqa: E402
 
 GOLDEN_DIR = REPO / "tests" / "golden"

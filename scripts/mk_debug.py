@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import mistral_inference_b200 as mi  # noqa: E402
-from mistral_inference_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 from mistral_inference_b200.cache import BufferCache  # noqa: E402
 from mistral_inference_b200.transformer import Transformer  # noqa: E402
 

@@ -7,7 +7,8 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import bench  # noqa: E402
-from mistral_inference_b200 import _abi, synth  # noqa: E402
+import synth  # noqa: E402
+from mistral_inference_b200 import _abi  # noqa: E402
 from mistral_inference_b200.cache import BufferCache  # noqa: E402
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -1,5 +1,7 @@
 """Deterministic synthetic checkpoints ("random-init" model folders) for tests and benchmarks.
 
+Fixture generator, NOT part of the product package: imported by bench.py, tests/, oracle/make_golden.py and scripts/ only.
+
 There is no network for real checkpoints, so every config in BASELINE.json runs on random-init
 weights of the named architecture.  Values come from a counter-based integer hash (splitmix64)
 evaluated with torch int64 ops, so the same (key, seed) gives bit-identical tensors on CPU and on

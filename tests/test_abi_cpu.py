@@ -9,7 +9,8 @@ import pytest
 import torch
 
 import mistral_inference_b200 as mi
-from mistral_inference_b200 import _abi, synth
+import synth
+from mistral_inference_b200 import _abi
 from mistral_inference_b200.build import build_library
 from mistral_inference_b200.cache import BufferCache
 from mistral_inference_b200.transformer import Transformer
@@ -129,7 +130,7 @@ def test_load_lora_merges_like_the_reference():
     import torch
 
     import mistral_inference_b200 as mi
-    from mistral_inference_b200 import synth
+    import synth
     from mistral_inference_b200.transformer import Transformer
 
     p = synth.shape("tiny-moe", n_layers=1)

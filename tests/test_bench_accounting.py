@@ -3,7 +3,7 @@ algorithmic bytes of one batch-1 decode step = every weight byte the step must r
 import math
 
 import bench
-from mistral_inference_b200 import synth
+import synth
 
 
 def _weight_bytes_from_shapes(p: dict) -> int:

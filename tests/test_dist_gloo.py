@@ -24,7 +24,7 @@ def _worker(rank: int, world: int, port: int, q):
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     import mistral_inference_b200 as mi
-    from mistral_inference_b200 import synth
+    import synth
     from mistral_inference_b200.transformer import Transformer
 
     my_ms = 100.0 + 25.0 * rank  # rank 1 is the slow replica
@@ -68,7 +68,7 @@ def _moe_worker(rank: int, world: int, port: int, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
     import mistral_inference_b200 as mi
-    from mistral_inference_b200 import synth
+    import synth
     from mistral_inference_b200.transformer import Transformer
     from oracle import restatement as R
     from tests.util import moe_plan_host, moe_route_host

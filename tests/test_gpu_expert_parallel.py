@@ -38,7 +38,7 @@ def _worker(rank: int, world: int, port: int, q, backend: str, top_k: int):
         else:
             torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
         import mistral_inference_b200 as mi
-        from mistral_inference_b200 import synth
+        import synth
         from mistral_inference_b200.cache import BufferCache
         from mistral_inference_b200.transformer import Transformer
 
@@ -119,7 +119,7 @@ def _pp_worker(rank: int, world: int, port: int, q, backend: str):
         else:
             torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
         import mistral_inference_b200 as mi
-        from mistral_inference_b200 import synth
+        import synth
         from mistral_inference_b200.transformer import Transformer
 
         p = synth.shape("tiny", n_layers=4, sliding_window=16)

@@ -18,7 +18,7 @@ import pytest
 import torch
 
 import mistral_inference_b200 as mi
-from mistral_inference_b200 import synth
+import synth
 from mistral_inference_b200.cache import BufferCache
 from mistral_inference_b200.transformer import Transformer
 from oracle import restatement as R

@@ -3,7 +3,7 @@ behind oracle/ref_shims.py).  Needs /root/reference, so it runs in the build con
 import pytest
 import torch
 
-from mistral_inference_b200 import synth
+import synth
 from oracle import ref_shims
 from oracle import restatement as R
 

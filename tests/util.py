@@ -5,7 +5,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from mistral_inference_b200 import synth
+import synth
 from oracle import restatement as R
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
