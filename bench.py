@@ -295,16 +295,7 @@ def run_ours(a, rank: int, world: int):
     prefill_ms = max_over_ranks(sorted(times)[1], world, model.device)
     pf = prefill_flops(p, a.prefill) * a.batch  # the lm head runs on every row in both variants (forward_logprobs: block by block)
 
-    # ---- decode: device-resident loop (value) ----
     megakernel = model._megakernel_ok(a.batch)
-    st0 = moe_stats(model, a.batch)
-    dec_ms, kern_us, clocks, tok = timed_decode(model, cache, tok, a.steps, a.warmup, world, dev_index)
-    st1 = moe_stats(model, a.batch)
-    touched = (st1[0] - st0[0]) / (st1[1] - st0[1]) if st1[1] > st0[1] else None  # measured distinct experts per MoE layer call
-    ms_per_step = dec_ms / a.steps
-    value = whole_job_tokens_per_s(replicas, a.batch, a.steps, dec_ms)
-    kv_len = min(W, a.prefill + max(a.warmup, 3) + a.steps / 2.0)
-    step_bytes = decode_bytes_per_step(p, kv_len, a.batch, touched)
     peaks = measured_peaks()
     n_gpus_bw = world if expert else 1
 
@@ -338,6 +329,18 @@ def run_ours(a, rank: int, world: int):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, model.device)
     e2e_val = whole_job_tokens_per_s(replicas, a.batch, a.steps, e2e_s * 1000.0)
+    tok = host_tok.to(model.device)
+
+    # ---- decode: device-resident loop (value).  Runs after the end-to-end loop: the first decode steps right after the prefills of a
+    # fresh process were measured up to 5 % slower than steady state on some boxes; W warm-up steps still precede the K timed ones ----
+    st0 = moe_stats(model, a.batch)
+    dec_ms, kern_us, clocks, tok = timed_decode(model, cache, tok, a.steps, a.warmup, world, dev_index)
+    st1 = moe_stats(model, a.batch)
+    touched = (st1[0] - st0[0]) / (st1[1] - st0[1]) if st1[1] > st0[1] else None  # measured distinct experts per MoE layer call
+    ms_per_step = dec_ms / a.steps
+    value = whole_job_tokens_per_s(replicas, a.batch, a.steps, dec_ms)
+    kv_len = min(W, a.prefill + 3 + a.steps + max(a.warmup, 3) + a.steps / 2.0)  # prefill + the e2e loop's steps + warm-up + half of the timed loop
+    step_bytes = decode_bytes_per_step(p, kv_len, a.batch, touched)
 
     parity = None
     if rank == 0 and megakernel and not a.no_parity:
