@@ -265,6 +265,7 @@ class Transformer(nn.Module):
             states[(id(self), key)] = st
         return st
 
+    @torch.inference_mode()
     def _decode_megakernel(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
         """Batch-1 decode step as ONE persistent cooperative kernel (csrc/decode_megakernel.cuh)."""
         import numpy as np
@@ -318,6 +319,7 @@ class Transformer(nn.Module):
         self._last_static_logits = st["logits"].data_ptr()
         return st["logits"]
 
+    @torch.inference_mode()
     def decode_static(self, tokens: torch.Tensor, cache: BufferCache) -> torch.Tensor:
         """One decode step for every sequence of `cache` (one new token each).  Batch 1: the persistent megakernel.  Batch > 1:
         the per-layer kernels replayed from a CUDA graph.  The step state lives on the DEVICE: `mb200_decode_meta` derives
