@@ -102,6 +102,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout_s: float = 3.0):
+        """nvidia-smi needs a few hundred ms to start: without this a 60 ms timed region ends before the first sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+        self.rows.clear()  # samples from before the load started are not "under load"
+
     def __exit__(self, *exc):
         if self.proc:
             time.sleep(0.15)
@@ -181,13 +188,15 @@ def timed_decode(model, cache, tok, steps: int, warmup: int, world: int, dev_ind
             model.decode_static(t, cache)
         return model.last_argmax  # greedy pick made on the device (fused in the decode kernel / in the step's graph)
 
-    for _ in range(max(warmup, 3)):
-        tok = step(tok)
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(dev_index) as clocks:
+    with ClockSampler(dev_index) as clocks:  # started before the warm-up so that it is sampling when the (short) timed region runs
+        if sample_clocks:
+            clocks.wait_first()
+        for _ in range(max(warmup, 3)):
+            tok = step(tok)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
         e0.record()
         for _ in range(steps):
             tok = step(tok, timed=True)
@@ -256,7 +265,7 @@ def run_ours(a, rank: int, world: int):
     expert = a.parallel == "expert" and world > 1
     model = build_gpu_model(p, a.batch, expert_parallel=(rank, world) if expert else None)
     replicas = 1 if expert else world
-    max_seq = a.prefill + 2 * (a.steps + max(a.warmup, 3)) + 64
+    max_seq = a.prefill + 2 * (a.steps + max(a.warmup, 32)) + 64
     W = p.get("sliding_window") or max_seq
 
     def fresh_cache():
@@ -318,7 +327,8 @@ def run_ours(a, rank: int, world: int):
         torch.cuda.synchronize()
         host_tok[:] = host_out[:, 0].long()
 
-    for _ in range(3):
+    e2e_warmup = max(32, a.warmup)  # the first decode steps after the prefills of a fresh process run up to 5 % slow: settle first
+    for _ in range(e2e_warmup):
         e2e_step()
     if world > 1:
         torch.distributed.barrier()
@@ -339,7 +349,7 @@ def run_ours(a, rank: int, world: int):
     touched = (st1[0] - st0[0]) / (st1[1] - st0[1]) if st1[1] > st0[1] else None  # measured distinct experts per MoE layer call
     ms_per_step = dec_ms / a.steps
     value = whole_job_tokens_per_s(replicas, a.batch, a.steps, dec_ms)
-    kv_len = min(W, a.prefill + 3 + a.steps + max(a.warmup, 3) + a.steps / 2.0)  # prefill + the e2e loop's steps + warm-up + half of the timed loop
+    kv_len = min(W, a.prefill + e2e_warmup + a.steps + max(a.warmup, 3) + a.steps / 2.0)  # prefill + the e2e loop's steps + warm-up + half of the timed loop
     step_bytes = decode_bytes_per_step(p, kv_len, a.batch, touched)
 
     parity = None
@@ -400,6 +410,7 @@ def run_ours(a, rank: int, world: int):
                    "decode_launch": "one persistent cooperative kernel per token (decode_megakernel)" if megakernel else "one CUDA-graph launch per step (device-side step state)",
                    "valid": a.layers in (None, 0)},
         "e2e": {"value": round(e2e_val, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8 * a.batch, "d2h_bytes_per_step": 8 * a.batch,
+                "warmup": e2e_warmup,
                 "api": "Transformer.next_token_logits(pinned host token -> H2D, cache) + device pick + mb200_logprob_gather, (token, logprob) D2H, synchronised every step"},
         "gpu_launches": a.steps * (1 if megakernel else per_layer * L + 4),
         "clocks": clocks,
