@@ -115,21 +115,6 @@ int mb200_linear_residual(const void* x, const void* w, const void* residual, vo
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Second half of a dense transformer block in ONE launch:
- *     h = x + attn_out @ wo^T;  g = silu(RMSNorm(h) @ w1^T) * (RMSNorm(h) @ w3^T);  out = h + g @ w2^T
- * Replaces transformer_layers.py:93,166-168 (wo + residual, ffn_norm, FeedForward :106, residual).
- *   attn_out [T, q_dim]; wo [dim, q_dim]; x, h, out [T, dim] (h aliases neither x nor out); w13 [2*hidden, dim] packed as for
- *   mb200_ffn_gateup; w2 [dim, hidden]; g [T, hidden] scratch.
- * For decode-sized batches (5 <= T <= 64, shapes that give every SM work in each phase) this is one persistent kernel whose
- * phases are separated by grid barriers while the weight stream runs through them (csrc/ffn_block.cuh); otherwise it is
- * exactly mb200_linear_residual + mb200_ffn_gateup + mb200_linear_residual.  Results are bit-identical either way.
- * MB200_FFN_BLOCK=0 in the environment forces the three separate launches.
- */
-int mb200_ffn_block(const void* attn_out, const void* wo, const void* x, const void* ffn_norm_w, const void* w13, const void* w2, void* h,
-                    void* g, void* out, int64_t T, int64_t dim, int64_t q_dim, int64_t hidden, float eps, void* workspace,
-                    size_t workspace_bytes, void* stream);
-
-/* ---------------------------------------------------------------------------------------------
  * Fused FFN input: RMSNorm -> packed gate/up projection -> bf16(silu(a)) * b.
  * Replaces ffn_norm + w1, w3, silu, mul (transformer_layers.py:167,106).
  *   x [T, dim]; norm_w [dim] (NULL = x is already normed, used by MoE experts);

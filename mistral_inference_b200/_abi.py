@@ -32,7 +32,6 @@ _SIGNATURES = {
                                   c_int64, c_void_p, c_size_t, c_void_p]),
     "mb200_attn_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
-    "mb200_ffn_block": (c_int, [c_void_p] * 9 + [c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "mb200_linear_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "mb200_ffn_gateup": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_size_t,
                                  c_void_p]),
@@ -202,14 +201,6 @@ def linear_residual(x, w, residual, out, ws: Workspace) -> None:
     N = w.shape[0]
     _check(lib().mb200_linear_residual(_ptr(x), _ptr(w), _ptr(residual), _ptr(out), T, N, K, ws.ptr, ws.nbytes, _stream()),
            "mb200_linear_residual")
-
-
-def ffn_block(attn_out, wo, x, norm_w, w13, w2, h, g, out, eps, ws: Workspace) -> None:
-    """h = x + attn_out @ wo^T; out = h + FeedForward(RMSNorm(h)) -- one persistent kernel at decode-sized batches."""
-    T, q_dim = attn_out.shape
-    dim, hidden = wo.shape[0], w2.shape[1]
-    _check(lib().mb200_ffn_block(_ptr(attn_out), _ptr(wo), _ptr(x), _ptr(norm_w), _ptr(w13), _ptr(w2), _ptr(h), _ptr(g), _ptr(out), T, dim, q_dim,
-                                 hidden, eps, ws.ptr, ws.nbytes, _stream()), "mb200_ffn_block")
 
 
 def ffn_gateup(x, norm_w, w13, g_out, eps, ws: Workspace) -> None:

@@ -9,7 +9,6 @@
 #include "attn_prefill_tcgen05.cuh"
 #include "decode_megakernel.cuh"
 #include "elementwise.cuh"
-#include "ffn_block.cuh"
 #include "gemm_mma.cuh"
 #include "gemm_streamk.cuh"
 #include "gemm_tcgen05.cuh"
@@ -263,19 +262,6 @@ int mb200_ffn_gateup(const void* x, const void* norm_w, const void* w13, void* g
   e.out = g_out;
   e.ld_out = hidden;
   return run_linear<EPI_SWIGLU>(x, norm_w, w13, e, T, 2 * hidden, dim, eps, workspace, workspace_bytes, (cudaStream_t)stream);
-}
-
-int mb200_ffn_block(const void* attn_out, const void* wo, const void* x, const void* ffn_norm_w, const void* w13, const void* w2, void* h, void* g,
-                    void* out, int64_t T, int64_t dim, int64_t q_dim, int64_t hidden, float eps, void* workspace, size_t workspace_bytes, void* stream) {
-  MB_CHECK_ARG(attn_out && wo && x && ffn_norm_w && w13 && w2 && h && g && out, "ffn_block: null pointer");
-  MB_CHECK_ARG(h != x && out != h, "ffn_block: h must not alias x or out (h is read as the second residual)");
-  if (ffn_block_eligible(T, dim, q_dim, hidden))
-    return launch_ffn_block(attn_out, wo, x, ffn_norm_w, w13, w2, h, g, out, T, dim, q_dim, hidden, eps, workspace, workspace_bytes, kWsHeader, (cudaStream_t)stream);
-  int rc = mb200_linear_residual(attn_out, wo, x, h, T, dim, q_dim, workspace, workspace_bytes, stream);
-  if (rc) return rc;
-  rc = mb200_ffn_gateup(h, ffn_norm_w, w13, g, T, dim, hidden, eps, workspace, workspace_bytes, stream);
-  if (rc) return rc;
-  return mb200_linear_residual(g, w2, h, out, T, dim, hidden, workspace, workspace_bytes, stream);
 }
 
 int mb200_lm_head(const void* x, const void* norm_w, const void* w_out, float* logits, int64_t T, int64_t dim, int64_t vocab, float eps,

@@ -28,26 +28,12 @@ constexpr int SK_MAX_CTAS = 160;
 constexpr size_t SK_PARTIAL_BYTES = (size_t)SK_MAX_CTAS * 128 * SK_BN * sizeof(float);  // one [128 x 128] fp32 slot per CTA
 constexpr size_t SK_FLAGS_OFFSET = 24576;  // inside the zero-initialised workspace header: uint32 flags[SK_MAX_CTAS]
 
-constexpr size_t SK_PROGRESS_OFFSET = 27136;  // workspace header: uint32 started (+0) and done (+128 B) counts of the weight streams
-
 struct SkParams {
   int T, N, K;
   EpiParams epi;
   float* partials;  // [gridDim][TA][128] fp32
   unsigned* flags;  // [gridDim], zero between launches
-  // L2 prefetch of this launch's next weight tiles while the PREVIOUS weight-streaming launch drains (see sk_l2_prefetch below)
-  unsigned* progress = nullptr;  // [0]: producers started, [32]: producers finished issuing; both monotonic, + gridDim per launch
-  int prefetch_boxes = 0;        // W boxes (16 KB each) per CTA beyond its first ring; 0 = off
 };
-
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
 
 template <int MODE, int TA, bool GROUPED>
 __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUtensorMap* map_w_base, const SkParams& p, const int32_t* plan) {
@@ -87,11 +73,6 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
-  // position of this launch among the weight-streaming launches on this workspace: a dependent grid starts only after every CTA
-  // of this one has passed the trigger below, so counts [m * G, (m + 1) * G) belong to the m-th launch
-  unsigned my_start = 0;
-  const bool l2_prefetch = !GROUPED && p.prefetch_boxes > 0;
-  if (l2_prefetch && threadIdx.x == 64) my_start = atomicAdd(p.progress, 1u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -130,7 +111,6 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         issue(it, true, true);
       }
-      if (l2_prefetch) atomicAdd(p.progress + 32, 1u);  // this SM's share of the weights is requested: successors may prefetch
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
@@ -160,25 +140,6 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
   } else {
     // ================= epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. + 31 =================
     const int lane_base = (warp & 3) * 32;
-    if (l2_prefetch && threadIdx.x == 64) {
-      // ---- L2 prefetch.  Between two dependent weight-streaming launches HBM idles for several microseconds: the predecessor's
-      // last tiles go through MMA, split-tile reduction, epilogue and grid completion before this launch's A tiles may be read,
-      // and the first ring (requested by the producer above) covers < 2 us of HBM time.  This thread -- idle until the first
-      // accumulator is ready -- waits until most SMs of the PREVIOUS weight-streaming launch have requested their last tile
-      // (earlier the prefetch would only take bandwidth from it, and a long predecessor would evict the lines again), then asks
-      // for the next `prefetch_boxes` W tiles of this CTA's range to be brought into L2, where the ring finds them.
-      // Predecessors that stream no weights (attention, norm) leave the counts equal: the prefetch starts at once.
-      const uint32_t n_it = (uint32_t)(u_end - u_begin), head = n_it < (uint32_t)STAGES ? n_it : (uint32_t)STAGES;
-      const uint32_t n_pf = min((uint32_t)p.prefetch_boxes, n_it - head);
-      if (n_pf > 0) {
-        const unsigned need = (my_start / (unsigned)G) * (unsigned)G - (unsigned)(G / 4);
-        while ((int)(ld_acquire_u32(p.progress + 32) - need) < 0 && !mbar_test(&tmem_full[0], 0)) __nanosleep(200);
-        for (uint32_t j = 0; j < n_pf; ++j) {
-          const uint32_t u = (uint32_t)u_begin + head + j;
-          tma_prefetch_l2_2d(map_w_base, (int)(u % (uint32_t)num_k) * TG_BK, (int)(u / (uint32_t)num_k) * SK_BN);
-        }
-      }
-    }
     if (!GROUPED) pdl_wait();  // stores below must not pass the predecessor's reads of the same buffers (returns at once when it is done)
     const bool row_ok = TA == 128 || lane_base + lane < TA;  // accumulator rows >= TA come from beyond the short A box
     const int etid = (int)threadIdx.x - 64;                  // 0..127 among the epilogue threads
@@ -285,15 +246,6 @@ inline bool streamk_eligible(int64_t T, int64_t N, int64_t K) {
 }
 
 // workspace: partial slots at `ws + header`, flags in the header (both overlap scratch of other, stream-ordered entry points)
-inline int sk_prefetch_boxes() {
-  static int n = [] {
-    const char* e = getenv("MB200_SK_PREFETCH");  // W boxes of 16 KB per CTA; 0 disables
-    const int v = e != nullptr ? atoi(e) : 16;
-    return v < 0 ? 0 : (v > 256 ? 256 : v);
-  }();
-  return n;
-}
-
 template <int MODE, int TA>
 int launch_streamk_ta(const GemmParams& g, void* workspace, size_t workspace_bytes, size_t header, cudaStream_t stream) {
   using Cfg = TgCfg<SK_BN, TA>;
@@ -316,10 +268,6 @@ int launch_streamk_ta(const GemmParams& g, void* workspace, size_t workspace_byt
   p.flags = reinterpret_cast<unsigned*>((uint8_t*)workspace + SK_FLAGS_OFFSET);
   const long long units = (long long)(g.N / SK_BN) * (g.K / TG_BK);
   const int grid = (int)(units < sms ? units : sms);
-  if (grid == sms) {  // the launch counts rely on every participating launch having the same number of CTAs
-    p.progress = reinterpret_cast<unsigned*>((uint8_t*)workspace + SK_PROGRESS_OFFSET);
-    p.prefetch_boxes = sk_prefetch_boxes();
-  }
   MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_streamk_kernel<MODE, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   MB_CHECK_CUDA(launch_pdl(gemm_streamk_kernel<MODE, TA>, dim3((unsigned)grid), dim3(TG_THREADS), (size_t)Cfg::kSmem, stream, map_a, map_w, p));
   return MB200_OK;

@@ -175,13 +175,6 @@ class TransformerBlock(nn.Module):
         # r = attention(attention_norm(x)); h = x + r        (transformer_layers.py:165-166)
         a = self.attention.attend(x, self.attention_norm.weight, self.norm_eps, rope, positions, cache, ws)
         h = torch.empty_like(x)
-        ff = self.feed_forward
-        if not isinstance(ff, MoeLayer) and 5 <= x.shape[0] <= 64:
-            # batched decode: wo + residual, ffn_norm, FeedForward and residual in one persistent kernel (csrc/ffn_block.cuh)
-            g = torch.empty(x.shape[0], ff.hidden_dim, dtype=x.dtype, device=x.device)
-            out = torch.empty_like(x)
-            _abi.ffn_block(a, self.attention.wo_weight, x, self.ffn_norm.weight, ff.w13, ff.w2_weight, h, g, out, self.norm_eps, ws)
-            return out
         _abi.linear_residual(a, self.attention.wo_weight, x, h, ws)
         # r = feed_forward(ffn_norm(h)); out = h + r          (transformer_layers.py:167-168)
         if isinstance(self.feed_forward, MoeLayer):

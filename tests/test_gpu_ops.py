@@ -369,46 +369,6 @@ def test_small_batch_gemm_tile_widths_agree(ws, monkeypatch, rope):
             assert torch.equal(a, b), f"{what}: tile width {bn} differs from 32"
 
 
-@pytest.mark.parametrize("T,dim,q_dim,hidden", [(32, 5120, 4096, 14336), (7, 5120, 4096, 14336), (64, 4096, 4096, 14336), (33, 4096, 4096, 14336),
-                                                (8, 6144, 6144, 16384), (16, 1024, 1024, 4096)])
-def test_ffn_block_equals_separate_launches(T, dim, q_dim, hidden, monkeypatch):
-    """The persistent wo + residual + ffn_norm + FeedForward + residual kernel (csrc/ffn_block.cuh) against the three separate
-    launches it replaces: bit-identical h and out (same unit partition, accumulation and summation order), over repeated launches
-    (the grid-barrier counter and the split-tile flags carry over), and rows >= T untouched.  The separate launches are checked
-    against the oracle above and in test_gpu_model.py."""
-    ws = _abi.Workspace(_abi.workspace_bytes(64, dim, q_dim // 128, 8, 128, hidden, 32000, 64), torch.device(DEV))
-    a = rnd(T, q_dim, seed=70).to(DEV)
-    x = rnd(T, dim, seed=71).to(DEV)
-    wo = rnd(dim, q_dim, seed=72, scale=q_dim ** -0.5).to(DEV)
-    nw = (1 + 0.2 * rnd(dim, seed=73).float()).to(torch.bfloat16).to(DEV)
-    w13 = rnd(2 * hidden, dim, seed=74, scale=dim ** -0.5).to(DEV)
-    w2 = rnd(dim, hidden, seed=75, scale=hidden ** -0.5).to(DEV)
-
-    def run(x_in):
-        h = torch.full((T + 2, dim), float("nan"), dtype=torch.bfloat16, device=DEV)
-        out = torch.full((T + 2, dim), float("nan"), dtype=torch.bfloat16, device=DEV)
-        g = torch.empty(T, hidden, dtype=torch.bfloat16, device=DEV)
-        _abi.ffn_block(a, wo, x_in, nw, w13, w2, h[:T], g, out[:T], 1e-5, ws)
-        torch.cuda.synchronize()
-        assert torch.isnan(h[T:].float()).all() and torch.isnan(out[T:].float()).all(), "rows past T were written"
-        return h[:T].clone(), g, out[:T].clone()
-
-    monkeypatch.setenv("MB200_FFN_BLOCK", "0")
-    h0, g0, o0 = run(x)
-    h0b, _, o0b = run(o0)  # a second, different input: stale state in the workspace would show
-    monkeypatch.setenv("MB200_FFN_BLOCK", "1")
-    for it in range(3):
-        h1, g1, o1 = run(x)
-        assert torch.equal(h0, h1), f"h differs (launch {it}): max {float((h0.float() - h1.float()).abs().max())}"
-        assert torch.equal(g0, g1), f"g differs (launch {it})"
-        assert torch.equal(o0, o1), f"out differs (launch {it}): max {float((o0.float() - o1.float()).abs().max())}"
-        h1b, _, o1b = run(o1)
-        assert torch.equal(h0b, h1b) and torch.equal(o0b, o1b), f"second input differs (launch {it})"
-    # and the first phase against torch directly
-    hf = x.cpu() + F.linear(a.cpu(), wo.cpu())
-    assert_bf16_close(h1, hf, atol=2 * 2 ** -8 * hf.abs().max().item(), what="ffn_block h")
-
-
 # ----------------------------------------------------------------------------- device-side step state, token selection, log-probs
 def test_decode_meta_matches_host_metadata():
     """mb200_decode_meta == BufferCache.build_metadata_host for one-token steps (cache.py:197-263), and it advances the positions."""
