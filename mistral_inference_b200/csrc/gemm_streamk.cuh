@@ -186,23 +186,71 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
           }
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
+        // The contributors' slots are summed by ALL 128 epilogue threads, 32 rows per pass: thread (r, cg) takes row r, columns
+        // 32 cg .. 32 cg + 31 of every contributor -- two contributors per round trip to L2, in ascending k order -- and parks the
+        // sum in shared memory (this is the CTA's last segment: every MMA has completed, the ring is free).  The warp that owns the
+        // pass's TMEM lanes then adds its accumulator and runs the epilogue.  (One thread per row walking 4 chunks x n contributors
+        // was a chain of ~12 dependent L2 round trips, 6-8 us at the end of every wo / down / qkv launch.)
+        {
+          constexpr int SROW = SK_BN + 4;  // floats: a 528-byte row stride keeps the 16-byte accesses of both sides conflict-free
+          float* stage = reinterpret_cast<float*>(smem);
+          const int r = etid & 31, cg = etid >> 5, n_o = last - cta;
+          const size_t slot = (size_t)TA * SK_BN;
 #pragma unroll 1
-        for (int c = 0; c < SK_BN / 32; ++c) {
-          tmem_ld_32x32b_x32(trow + c * 32, v);
-          if (lane_base < TA) {
-            for (int o = cta + 1; o <= last; ++o) {
-              const float* theirs = p.partials + ((size_t)o * TA + lane_base + lane) * SK_BN + c * 32;
+          for (int ps = 0; ps < TA / 32; ++ps) {
+            const float* src = p.partials + ((size_t)(cta + 1) * TA + ps * 32 + r) * SK_BN + cg * 32;
+            float sum[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src) + q);
+              sum[4 * q] = __uint_as_float(w.x), sum[4 * q + 1] = __uint_as_float(w.y), sum[4 * q + 2] = __uint_as_float(w.z), sum[4 * q + 3] = __uint_as_float(w.w);
+            }
+            int o = 1;
+#pragma unroll 1
+            for (; o + 1 < n_o; o += 2) {
+              uint4 w0[8], w1[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const uint4 w = __ldcg(reinterpret_cast<const uint4*>(theirs) + q);
-                v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + __uint_as_float(w.x));
-                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + __uint_as_float(w.y));
-                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + __uint_as_float(w.z));
-                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + __uint_as_float(w.w));
+                w0[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
+                w1[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(o + 1) * slot) + q);
+              }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                sum[4 * q] = (sum[4 * q] + __uint_as_float(w0[q].x)) + __uint_as_float(w1[q].x);
+                sum[4 * q + 1] = (sum[4 * q + 1] + __uint_as_float(w0[q].y)) + __uint_as_float(w1[q].y);
+                sum[4 * q + 2] = (sum[4 * q + 2] + __uint_as_float(w0[q].z)) + __uint_as_float(w1[q].z);
+                sum[4 * q + 3] = (sum[4 * q + 3] + __uint_as_float(w0[q].w)) + __uint_as_float(w1[q].w);
               }
             }
+            if (o < n_o) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
+                sum[4 * q] += __uint_as_float(w.x), sum[4 * q + 1] += __uint_as_float(w.y), sum[4 * q + 2] += __uint_as_float(w.z), sum[4 * q + 3] += __uint_as_float(w.w);
+              }
+            }
+            float4* dst = reinterpret_cast<float4*>(stage + r * SROW + cg * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (lane_base == ps * 32) {  // warp-uniform: this warp's TMEM lanes are the rows of this pass
+#pragma unroll 1
+              for (int c = 0; c < SK_BN / 32; ++c) {
+                tmem_ld_32x32b_x32(trow + c * 32, v);
+                const float4* rest = reinterpret_cast<const float4*>(stage + lane * SROW + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 w = rest[q];
+                  v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + w.x);
+                  v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + w.y);
+                  v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + w.z);
+                  v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + w.w);
+                }
+                if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
+              }
+            }
+            if (ps + 1 < TA / 32) asm volatile("bar.sync 2, 128;" ::: "memory");  // the next pass reuses the staging rows
           }
-          if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
         if (etid == 0)
