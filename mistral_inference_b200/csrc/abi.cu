@@ -581,3 +581,15 @@ int mb200_test_gemm_naive(const void* a, const void* w, float* c, int64_t T, int
 }
 
 }  // extern "C"
+
+#ifdef MB200_SK_TRACE
+// tracing build only (scripts/trace_streamk.py): copies the stream-K stamp ring to the host and returns the stamp count
+extern "C" int mb200_debug_sk_trace(void* host_out, size_t bytes, unsigned* count) {
+  using namespace mb200;
+  if (bytes < sizeof(sk_trace_buf)) return fail(MB200_E_INVALID, "sk trace: %zu < %zu", bytes, sizeof(sk_trace_buf));
+  MB_CHECK_CUDA(cudaDeviceSynchronize());
+  MB_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, sk_trace_buf, sizeof(sk_trace_buf)));
+  MB_CHECK_CUDA(cudaMemcpyFromSymbol(count, sk_trace_count, sizeof(unsigned)));
+  return MB200_OK;
+}
+#endif

@@ -103,6 +103,26 @@ __device__ __forceinline__ uint32_t pack2_rn(float lo, float hi) {
 }
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// What epi_chunk32 will READ for row t, columns n0 .. n0 + 127, requested ahead of time (the thread is about to wait for its
+// accumulator): the residual row segment, or the row's position and its RoPE table lines.  Prefetches only -- no registers held.
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+template <int MODE>
+__device__ __forceinline__ void epi_prefetch128(const EpiParams& p, int t, int n0) {
+  if constexpr (MODE == EPI_RESIDUAL) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)t * p.ld_out + n0);
+    prefetch_l1(src);
+    prefetch_l1(src + 128);
+  } else if constexpr (MODE == EPI_QKV_ROPE) {
+    if (n0 < p.q_dim + p.kv_dim) {
+      const int pos = p.positions[t];
+      const uint8_t* cs = reinterpret_cast<const uint8_t*>(p.rope + (int64_t)pos * kHeadDim);  // [n_pos, 64, 2] floats: 512 B per position
+#pragma unroll
+      for (int i = 0; i < 4; ++i) prefetch_l1(cs + 128 * i);
+    }
+    if (n0 >= p.q_dim && p.cache_rows != nullptr) prefetch_l1(p.cache_rows + t);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int t, int n, const uint32_t (&v)[32]) {
   if constexpr (MODE == EPI_STORE || MODE == EPI_RESIDUAL) {

@@ -28,6 +28,24 @@ constexpr int SK_MAX_CTAS = 160;
 constexpr size_t SK_PARTIAL_BYTES = (size_t)SK_MAX_CTAS * 128 * SK_BN * sizeof(float);  // one [128 x 128] fp32 slot per CTA
 constexpr size_t SK_FLAGS_OFFSET = 24576;  // inside the zero-initialised workspace header: uint32 flags[SK_MAX_CTAS]
 
+// -DMB200_SK_TRACE: every CTA of the dense kernel stamps %globaltimer / %clock64 at eight points of its life into a device ring
+// (scripts/trace_streamk.py reads it through mb200_debug_sk_trace) -- how the microseconds between dependent launches are spent.
+#ifdef MB200_SK_TRACE
+constexpr int SK_TRACE_LAUNCHES = 64, SK_TRACE_POINTS = 8;
+__device__ unsigned long long sk_trace_buf[SK_TRACE_LAUNCHES][SK_MAX_CTAS][SK_TRACE_POINTS][2];
+__device__ unsigned sk_trace_count;
+__device__ __forceinline__ void sk_stamp(unsigned launch, int point) {
+  unsigned long long g, c;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+  sk_trace_buf[launch % SK_TRACE_LAUNCHES][blockIdx.x][point][0] = g;
+  sk_trace_buf[launch % SK_TRACE_LAUNCHES][blockIdx.x][point][1] = c;
+}
+#define SK_STAMP(point) sk_stamp(*trace_launch, point)
+#else
+#define SK_STAMP(point) ((void)0)
+#endif
+
 struct SkParams {
   int T, N, K;
   EpiParams epi;
@@ -73,11 +91,19 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+#ifdef MB200_SK_TRACE
+  __shared__ unsigned trace_launch_slot;
+  if (threadIdx.x == 96) trace_launch_slot = atomicAdd(&sk_trace_count, 1u) / gridDim.x;  // all CTAs of a launch start before any of the next
+  volatile unsigned* trace_launch = &trace_launch_slot;
+#endif
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  if (threadIdx.x == 0) pdl_trigger();
+  if (threadIdx.x == 0) {
+    SK_STAMP(0);  // CTA set up
+    pdl_trigger();
+  }
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -104,6 +130,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         issue(it, false, true);
       }
       pdl_wait();
+      SK_STAMP(1);  // predecessor complete: A tiles may be requested
       for (uint32_t it = 0; it < head; ++it) issue(it, true, false);
       for (uint32_t it = head; it < n_it; ++it) {
         const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
@@ -111,6 +138,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         issue(it, true, true);
       }
+      SK_STAMP(3);  // last tile requested
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
@@ -126,6 +154,9 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
           mbar_wait(&full[s], par, 23, it);
+#ifdef MB200_SK_TRACE
+          if (it == 0) SK_STAMP(2);  // first stage landed: first MMA
+#endif
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_BYTES);
@@ -136,6 +167,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         umma_commit(&tmem_full[acc]);
         u += kb1 - kb0;
       }
+      SK_STAMP(4);  // last MMA issued
     }
   } else {
     // ================= epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. + 31 =================
@@ -149,9 +181,73 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
       const int kb1 = (int)min((long long)num_k, kb0 + (u_end - u));
       const int m0 = GROUPED ? tile_row0[tile % num_m] : 0, n0 = (tile / num_m) * SK_BN;
       const uint32_t acc = seg & 1, acc_par = (seg >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_par, 24, seg);
-      tc_fence_after();
+      // Split tiles.  A contributor that does not own the tile's first k-block parks its fp32 accumulator in its workspace slot;
+      // the owner adds the slots in ascending k order.  The slots are summed by ALL 128 epilogue threads, 32 rows per pass: thread
+      // (r, cg) takes row r, columns 32 cg .. + 31 of every contributor, two contributors per round trip to L2.  (One thread per
+      // row walking 4 chunks x n contributors was a chain of ~12 dependent L2 round trips: 6-8 us at the end of every launch.)
+      const bool owner = kb0 == 0 && kb1 != num_k;
+      int last = cta;
+      float sum[32];
+      auto sum_pass = [&](int ps) {
+        const int r = etid & 31, cg = etid >> 5, n_o = last - cta;
+        const size_t slot = (size_t)TA * SK_BN;
+        const float* src = p.partials + ((size_t)(cta + 1) * TA + ps * 32 + r) * SK_BN + cg * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src) + q);
+          sum[4 * q] = __uint_as_float(w.x), sum[4 * q + 1] = __uint_as_float(w.y), sum[4 * q + 2] = __uint_as_float(w.z), sum[4 * q + 3] = __uint_as_float(w.w);
+        }
+        int o = 1;
+#pragma unroll 1
+        for (; o + 1 < n_o; o += 2) {
+          uint4 w0[8], w1[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            w0[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
+            w1[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(o + 1) * slot) + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            sum[4 * q] = (sum[4 * q] + __uint_as_float(w0[q].x)) + __uint_as_float(w1[q].x);
+            sum[4 * q + 1] = (sum[4 * q + 1] + __uint_as_float(w0[q].y)) + __uint_as_float(w1[q].y);
+            sum[4 * q + 2] = (sum[4 * q + 2] + __uint_as_float(w0[q].z)) + __uint_as_float(w1[q].z);
+            sum[4 * q + 3] = (sum[4 * q + 3] + __uint_as_float(w0[q].w)) + __uint_as_float(w1[q].w);
+          }
+        }
+        if (o < n_o) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
+            sum[4 * q] += __uint_as_float(w.x), sum[4 * q + 1] += __uint_as_float(w.y), sum[4 * q + 2] += __uint_as_float(w.z), sum[4 * q + 3] += __uint_as_float(w.w);
+          }
+        }
+      };
+      if (owner) {
+        // The contributors did their share FIRST in their ranges, this tile is the LAST thing this CTA does: their slots are ready
+        // long before this CTA's own k-blocks are through the tensor core, so the first 32 rows are summed while those still run.
+        const long long tile_end = (long long)(tile + 1) * num_k;
+        while (last + 1 < G && first(last + 1) < tile_end) ++last;
+        if (etid == 0) {
+          for (int c = cta + 1; c <= last; ++c) {
+            unsigned spins = 0;
+            while (ld_acquire_u32(p.flags + c) == 0u) {
+              if (++spins == MB200_WATCHDOG_SPINS) {
+                printf("[mb200 watchdog] stream-K block %d waits for the partial of block %d (tile %d)\n", cta, c, tile);
+                __trap();
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        sum_pass(0);
+      }
       const int t = row_ok ? m0 + lane_base + lane : 0x7fffffff;
+      if (kb0 == 0 && t < p.T) epi_prefetch128<MODE>(p.epi, t, n0);  // this segment ends in an epilogue: its operands, while the MMAs run
+      mbar_wait(&tmem_full[acc], acc_par, 24, seg);
+#ifdef MB200_SK_TRACE
+      if (threadIdx.x == 64 && u + (kb1 - kb0) >= u_end) SK_STAMP(5);  // last accumulator complete
+#endif
+      tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16) + acc * SK_BN;
       uint32_t v[32];
       if (kb0 != 0) {
@@ -169,88 +265,35 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
         __threadfence();
         asm volatile("bar.sync 2, 128;" ::: "memory");
         if (etid == 0) st_release_u32(p.flags + cta, 1u);
-      } else if (kb1 != num_k) {
-        // ---- owner of the first k-block of a tile others finish: wait for them (they did it first thing), add in k order ----
-        const long long tile_end = (long long)(tile + 1) * num_k;
-        int last = cta;
-        while (last + 1 < G && first(last + 1) < tile_end) ++last;
-        if (etid == 0) {
-          for (int c = cta + 1; c <= last; ++c) {
-            unsigned spins = 0;
-            while (ld_acquire_u32(p.flags + c) == 0u) {
-              if (++spins == MB200_WATCHDOG_SPINS) {
-                printf("[mb200 watchdog] stream-K block %d waits for the partial of block %d (tile %d)\n", cta, c, tile);
-                __trap();
+      } else if (owner) {
+        // ---- owner: park the sums in shared memory (this is the CTA's last segment: every MMA has completed, the ring is
+        // free); the warp that owns the pass's TMEM lanes adds its accumulator and runs the epilogue ----
+        constexpr int SROW = SK_BN + 4;  // floats: a 528-byte row stride keeps the 16-byte accesses of both sides conflict-free
+        float* stage = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+        for (int ps = 0; ps < TA / 32; ++ps) {
+          if (ps > 0) sum_pass(ps);
+          float4* dst = reinterpret_cast<float4*>(stage + (etid & 31) * SROW + (etid >> 5) * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (lane_base == ps * 32) {  // warp-uniform: this warp's TMEM lanes are the rows of this pass
+#pragma unroll 1
+            for (int c = 0; c < SK_BN / 32; ++c) {
+              tmem_ld_32x32b_x32(trow + c * 32, v);
+              const float4* rest = reinterpret_cast<const float4*>(stage + lane * SROW + c * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w = rest[q];
+                v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + w.x);
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + w.y);
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + w.z);
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + w.w);
               }
+              if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
             }
           }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        // The contributors' slots are summed by ALL 128 epilogue threads, 32 rows per pass: thread (r, cg) takes row r, columns
-        // 32 cg .. 32 cg + 31 of every contributor -- two contributors per round trip to L2, in ascending k order -- and parks the
-        // sum in shared memory (this is the CTA's last segment: every MMA has completed, the ring is free).  The warp that owns the
-        // pass's TMEM lanes then adds its accumulator and runs the epilogue.  (One thread per row walking 4 chunks x n contributors
-        // was a chain of ~12 dependent L2 round trips, 6-8 us at the end of every wo / down / qkv launch.)
-        {
-          constexpr int SROW = SK_BN + 4;  // floats: a 528-byte row stride keeps the 16-byte accesses of both sides conflict-free
-          float* stage = reinterpret_cast<float*>(smem);
-          const int r = etid & 31, cg = etid >> 5, n_o = last - cta;
-          const size_t slot = (size_t)TA * SK_BN;
-#pragma unroll 1
-          for (int ps = 0; ps < TA / 32; ++ps) {
-            const float* src = p.partials + ((size_t)(cta + 1) * TA + ps * 32 + r) * SK_BN + cg * 32;
-            float sum[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-              sum[4 * q] = __uint_as_float(w.x), sum[4 * q + 1] = __uint_as_float(w.y), sum[4 * q + 2] = __uint_as_float(w.z), sum[4 * q + 3] = __uint_as_float(w.w);
-            }
-            int o = 1;
-#pragma unroll 1
-            for (; o + 1 < n_o; o += 2) {
-              uint4 w0[8], w1[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                w0[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
-                w1[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(o + 1) * slot) + q);
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                sum[4 * q] = (sum[4 * q] + __uint_as_float(w0[q].x)) + __uint_as_float(w1[q].x);
-                sum[4 * q + 1] = (sum[4 * q + 1] + __uint_as_float(w0[q].y)) + __uint_as_float(w1[q].y);
-                sum[4 * q + 2] = (sum[4 * q + 2] + __uint_as_float(w0[q].z)) + __uint_as_float(w1[q].z);
-                sum[4 * q + 3] = (sum[4 * q + 3] + __uint_as_float(w0[q].w)) + __uint_as_float(w1[q].w);
-              }
-            }
-            if (o < n_o) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
-                sum[4 * q] += __uint_as_float(w.x), sum[4 * q + 1] += __uint_as_float(w.y), sum[4 * q + 2] += __uint_as_float(w.z), sum[4 * q + 3] += __uint_as_float(w.w);
-              }
-            }
-            float4* dst = reinterpret_cast<float4*>(stage + r * SROW + cg * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]);
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (lane_base == ps * 32) {  // warp-uniform: this warp's TMEM lanes are the rows of this pass
-#pragma unroll 1
-              for (int c = 0; c < SK_BN / 32; ++c) {
-                tmem_ld_32x32b_x32(trow + c * 32, v);
-                const float4* rest = reinterpret_cast<const float4*>(stage + lane * SROW + c * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 w = rest[q];
-                  v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + w.x);
-                  v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + w.y);
-                  v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + w.z);
-                  v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + w.w);
-                }
-                if (t < p.T) epi_chunk32<MODE>(p.epi, t, n0 + c * 32, v);
-              }
-            }
-            if (ps + 1 < TA / 32) asm volatile("bar.sync 2, 128;" ::: "memory");  // the next pass reuses the staging rows
-          }
+          if (ps + 1 < TA / 32) asm volatile("bar.sync 2, 128;" ::: "memory");  // the next pass reuses the staging rows
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
         if (etid == 0)
@@ -268,10 +311,16 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       u += kb1 - kb0;
     }
+#ifdef MB200_SK_TRACE
+    if (threadIdx.x == 64) SK_STAMP(6);  // epilogues done
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+#ifdef MB200_SK_TRACE
+  if (threadIdx.x == 0) SK_STAMP(7);  // exit
+#endif
 }
 
 template <int MODE, int TA>
