@@ -191,50 +191,42 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
       auto sum_pass = [&](int ps) {
         const int r = etid & 31, cg = etid >> 5, n_o = last - cta;
         const size_t slot = (size_t)TA * SK_BN;
-        const float* src = p.partials + ((size_t)(cta + 1) * TA + ps * 32 + r) * SK_BN + cg * 32;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-          sum[4 * q] = __uint_as_float(w.x), sum[4 * q + 1] = __uint_as_float(w.y), sum[4 * q + 2] = __uint_as_float(w.z), sum[4 * q + 3] = __uint_as_float(w.w);
-        }
-        int o = 1;
+        const uint4* src = reinterpret_cast<const uint4*>(p.partials + ((size_t)(cta + 1) * TA + ps * 32 + r) * SK_BN + cg * 32);
+        // four contributors (usually all of them) per round trip: the 8 column groups are independent, so their loads overlap;
+        // the sum runs left to right over the contributors, i.e. in ascending k order
 #pragma unroll 1
-        for (; o + 1 < n_o; o += 2) {
-          uint4 w0[8], w1[8];
+        for (int ob = 0; ob < n_o; ob += 4) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            w0[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
-            w1[q] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(o + 1) * slot) + q);
-          }
+            uint4 w[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            sum[4 * q] = (sum[4 * q] + __uint_as_float(w0[q].x)) + __uint_as_float(w1[q].x);
-            sum[4 * q + 1] = (sum[4 * q + 1] + __uint_as_float(w0[q].y)) + __uint_as_float(w1[q].y);
-            sum[4 * q + 2] = (sum[4 * q + 2] + __uint_as_float(w0[q].z)) + __uint_as_float(w1[q].z);
-            sum[4 * q + 3] = (sum[4 * q + 3] + __uint_as_float(w0[q].w)) + __uint_as_float(w1[q].w);
-          }
-        }
-        if (o < n_o) {
+            for (int jj = 0; jj < 4; ++jj)
+              if (ob + jj < n_o) w[jj] = __ldcg(src + (size_t)(ob + jj) * (slot / 4) + q);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)o * slot) + q);
-            sum[4 * q] += __uint_as_float(w.x), sum[4 * q + 1] += __uint_as_float(w.y), sum[4 * q + 2] += __uint_as_float(w.z), sum[4 * q + 3] += __uint_as_float(w.w);
+            for (int jj = 0; jj < 4; ++jj) {
+              if (ob + jj < n_o) {
+                if (ob + jj == 0) {
+                  sum[4 * q] = __uint_as_float(w[jj].x), sum[4 * q + 1] = __uint_as_float(w[jj].y), sum[4 * q + 2] = __uint_as_float(w[jj].z), sum[4 * q + 3] = __uint_as_float(w[jj].w);
+                } else {
+                  sum[4 * q] += __uint_as_float(w[jj].x), sum[4 * q + 1] += __uint_as_float(w[jj].y), sum[4 * q + 2] += __uint_as_float(w[jj].z), sum[4 * q + 3] += __uint_as_float(w[jj].w);
+                }
+              }
+            }
           }
         }
       };
       if (owner) {
-        // The contributors did their share FIRST in their ranges, this tile is the LAST thing this CTA does: their slots are ready
-        // long before this CTA's own k-blocks are through the tensor core, so the first 32 rows are summed while those still run.
+        // Contributors holding the tile's tail did it FIRST in their ranges; those whose whole range lies inside this tile finish
+        // together with this CTA.  The flags are polled in parallel (one thread per contributor) and the first 32 rows are summed
+        // before this CTA's own accumulator is waited for.
         const long long tile_end = (long long)(tile + 1) * num_k;
         while (last + 1 < G && first(last + 1) < tile_end) ++last;
-        if (etid == 0) {
-          for (int c = cta + 1; c <= last; ++c) {
-            unsigned spins = 0;
-            while (ld_acquire_u32(p.flags + c) == 0u) {
-              if (++spins == MB200_WATCHDOG_SPINS) {
-                printf("[mb200 watchdog] stream-K block %d waits for the partial of block %d (tile %d)\n", cta, c, tile);
-                __trap();
-              }
+        for (int c = cta + 1 + etid; c <= last; c += 128) {
+          unsigned spins = 0;
+          while (ld_acquire_u32(p.flags + c) == 0u) {
+            if (++spins == MB200_WATCHDOG_SPINS) {
+              printf("[mb200 watchdog] stream-K block %d waits for the partial of block %d (tile %d)\n", cta, c, tile);
+              __trap();
             }
           }
         }
@@ -324,13 +316,13 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
 }
 
 template <int MODE, int TA>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__global__ void __launch_bounds__(TG_THREADS, 2)  // two CTAs per SM (the tail of one launch beside the head of the next): <= 168 registers
     gemm_streamk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const SkParams p) {
   sk_gemm_body<MODE, TA, false>(map_a, &map_w, p, nullptr);
 }
 
 template <int MODE, int TA>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__global__ void __launch_bounds__(TG_THREADS, 2)
     gemm_streamk_grouped_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ MoeWeightMaps maps_w, const SkParams p,
                                 const int32_t* __restrict__ plan) {
   sk_gemm_body<MODE, TA, true>(map_a, maps_w.m, p, plan);
