@@ -43,12 +43,23 @@ struct TgCfg {
   static constexpr int kABytes = TA * TG_BK * 2;
   static constexpr int kBBytes = BN * TG_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlack = TA < 128 ? TG_A_BYTES : 0;  // the last stage's M = 128 read must stay inside the allocation
+  // The MMA always reads M = 128 rows (16 KB) from a stage's A base; with a short A box that runs on into the stage's W tile
+  // (harmless: accumulator row i depends on A row i only) and, in the LAST stage, past it when the stage is smaller than 16 KB.
+  // A full 16 KB of slack is more than the 20-24 KB stages of the stream-K kernel need, and it is what keeps its CTAs at 117.5 KB:
+  // TWO of them do not fit an SM.  That is deliberate: with the exact slack (-DMB200_TIGHT_SLACK: 101.5 KB, the successor launch's
+  // CTA sits beside the running one from its start) the Nemo-12B batch-32 step measured 7.48 ms against 6.85 ms on the same box
+  // (call 22) -- the early CTA's ring fill and polling take bandwidth and issue slots from the launch that is on the critical path.
+  // As it is, a successor CTA starts when the predecessor's CTA on that SM exits, i.e. during the predecessor's reduction tail.
+#ifdef MB200_TIGHT_SLACK
+  static constexpr int kSlack = (TA < 128 && kStageBytes < TG_A_BYTES) ? TG_A_BYTES - kStageBytes : 0;
+#else
+  static constexpr int kSlack = TA < 128 ? TG_A_BYTES : 0;
+#endif
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - kSlack) / kStageBytes;
-  // decode-sized variants: the ring is capped at ~100 KB so that TWO CTAs fit one SM -- not two of the same launch (a launch has
-  // one CTA per SM) but the tail of one kernel and the head of the next: under programmatic dependent launch the successor's CTA
-  // moves in beside the running one, requests its first ring of weight tiles and waits; 80 KB in flight per CTA is still above
-  // the ~45-65 KB bandwidth-delay product of one SM's HBM share.
+  // decode-sized variants: a ring of ~100 KB (80 KB of weights in flight per CTA, above the ~45-65 KB bandwidth-delay product of
+  // one SM's HBM share) instead of the whole 227 KB: measured faster in a chain of dependent launches (scripts/bench_linear.py:
+  // qkv 24.0 -> 21.3 us, down 39.5 -> 36.8 us; only the 1.3 GB lm head loses 5 %) -- a successor's CTA, which starts when the
+  // predecessor's CTA on its SM exits, has its first ring filled sooner, and other decode kernels' CTAs fit beside it.
   static constexpr int kCoResidentStages = (100 * 1024) / kStageBytes;
   static constexpr int kStages = (TA < 128 || BN < 128) ? (kCoResidentStages < 3 ? 3 : (kCoResidentStages > kMaxStages ? kMaxStages : kCoResidentStages))
                                                         : (BN == 128 ? 6 : 4);
