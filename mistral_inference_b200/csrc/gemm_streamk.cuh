@@ -316,7 +316,7 @@ __device__ __forceinline__ void sk_gemm_body(const CUtensorMap& map_a, const CUt
 }
 
 template <int MODE, int TA>
-__global__ void __launch_bounds__(TG_THREADS, 2)  // two CTAs per SM (the tail of one launch beside the head of the next): <= 168 registers
+__global__ void __launch_bounds__(TG_THREADS, 2)  // <= 168 registers: the reduction's loads must not grow the footprint other decode kernels' CTAs share the SM with
     gemm_streamk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const SkParams p) {
   sk_gemm_body<MODE, TA, false>(map_a, &map_w, p, nullptr);
 }

@@ -60,8 +60,8 @@ struct TgCfg {
   // one SM's HBM share) instead of the whole 227 KB: measured faster in a chain of dependent launches (scripts/bench_linear.py:
   // qkv 24.0 -> 21.3 us, down 39.5 -> 36.8 us; only the 1.3 GB lm head loses 5 %) -- a successor's CTA, which starts when the
   // predecessor's CTA on its SM exits, has its first ring filled sooner, and other decode kernels' CTAs fit beside it.
-  static constexpr int kCoResidentStages = (100 * 1024) / kStageBytes;
-  static constexpr int kStages = (TA < 128 || BN < 128) ? (kCoResidentStages < 3 ? 3 : (kCoResidentStages > kMaxStages ? kMaxStages : kCoResidentStages))
+  static constexpr int kShortRingStages = (100 * 1024) / kStageBytes;
+  static constexpr int kStages = (TA < 128 || BN < 128) ? (kShortRingStages < 3 ? 3 : (kShortRingStages > kMaxStages ? kMaxStages : kShortRingStages))
                                                         : (BN == 128 ? 6 : 4);
   static constexpr int kSmem = kStages * kStageBytes + kSlack + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));  // 2 accumulators
