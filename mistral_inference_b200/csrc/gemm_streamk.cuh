@@ -8,11 +8,14 @@
 //   * N / 128 tiles do not divide over 148 SMs (wo of Nemo: 40 tiles; gate/up: 224 = 1.5 rounds), so the work is cut stream-K
 //     style instead: the (tile, k-block) units of the whole problem are one sequence, and CTA c takes the c-th contiguous 1/G of
 //     it -- every SM streams the same number of bytes (+- one 16 KB stage) in one pass, whatever N and K are.
-// A CTA's range covers the tail of one tile, some whole tiles and the head of another.  Partial tiles are reduced
-// deterministically: a contributor that does not own the tile's first k-block writes its fp32 accumulator to its own slot of the
-// workspace and raises a flag; the owner of the first k-block -- for which this tile is the LAST thing it does, long after the
-// others did theirs FIRST -- adds the partials in ascending k order and runs the epilogue.  No atomics on data, no host-visible
-// state: flags are consumed (reset) by their single reader.
+// A CTA's range covers the tail of one tile, some whole tiles and the head of another (or, when tiles are longer than ranges,
+// a piece from the middle of one).  Partial tiles are reduced deterministically: a contributor that does not hold the tile's
+// first k-block writes its fp32 accumulator to its own slot of the workspace and raises its flag -- always as the FIRST segment
+// of its range; the owner of the first k-block -- always as the LAST segment of its range -- waits for the flags, sums the slots
+// in ascending k order (all 128 epilogue threads, up to four contributors per L2 round trip), adds its own accumulator and runs
+// the epilogue.  No atomics on data, no host-visible state: flags are consumed (reset) by their single reader.  The partition
+// and the flag protocol are model-checked on the CPU in tests/test_streamk_protocol.py; scripts/trace_streamk.py (tracing build)
+// prints the time line of a chain of launches.
 //
 // Structure per CTA is that of gemm_tcgen05.cuh: warp 0 TMA producer ([TA x 64] A box + [128 x 64] W box per stage, deep ring),
 // warp 1 tcgen05.mma issuer (M = 128 -- rows >= TA read past the short A box and are never stored --, N = 128, fp32 accumulators
